@@ -1,0 +1,35 @@
+"""Generates tests/golden/oracle_sync_runs.json: iteration counts / residuals of the CPU oracle on small
+configurations.  These are regression fixtures OF THE ORACLE (the reference cannot run here: PETSc/MPICH
+absent), used to (a) detect drift of the oracle, (b) give the GPU parity tests fixed expectations."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle import oracle as O  # noqa: E402
+
+inner20 = dict(restart=30, max_it=20, rtol=1e-10, abstol=1e-100)
+inner50 = dict(restart=30, max_it=50, rtol=1e-10, abstol=1e-100)
+cases = [
+    dict(alg="SM", m=32, n=32, nblocks=2, s=0, rtol=1e-6, inner=inner50),
+    dict(alg="SM", m=48, n=32, nblocks=4, s=0, rtol=1e-5, inner=inner20),
+    dict(alg="SMSM_GLOBAL", m=32, n=32, nblocks=2, s=5, rtol=1e-6, inner=inner20),
+    dict(alg="SMSM_GLOBAL", m=64, n=64, nblocks=1, s=5, rtol=1e-6, inner=inner20),
+    dict(alg="SMSM_GLOBAL", m=64, n=64, nblocks=4, s=4, rtol=1e-5, inner=inner20),
+    dict(alg="SMSM_SEMI_LOCAL", m=32, n=32, nblocks=2, s=5, rtol=1e-6, inner=inner20),
+    dict(alg="SMSM_LOCAL", m=32, n=32, nblocks=2, s=5, rtol=1e-6, inner=inner20),
+    dict(alg="SMSM_GLOBAL", m=12, n=12, p=12, nblocks=2, s=5, rtol=1e-6, inner=inner20),
+    dict(alg="SMSM_SEMI_LOCAL", m=16, n=16, p=16, nblocks=2, s=5, rtol=1e-6, inner=dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)),
+]
+runs = []
+for c in cases:
+    r = O.solve(c["alg"], c["m"], c["n"], p=c.get("p", 1), nblocks=c["nblocks"], s=c["s"], rtol=c["rtol"], inner=c["inner"],
+                max_outer=3000)
+    assert r["rc"] == 0, c
+    d = dict(c)
+    d.update(outer_its=r["outer_its"], final_residual=r["final_residual"], last_norm=r["last_norm"], norm0=r["norm0"],
+             error=r["error"], inner_its_total=r["inner_its_total"])
+    runs.append(d)
+    print(d)
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_sync_runs.json"), "w") as f:
+    json.dump({"generator": "tests/golden/make_oracle_sync_runs.py", "runs": runs}, f, indent=1)

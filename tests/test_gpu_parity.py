@@ -1,0 +1,279 @@
+"""Parity tests proper: the CUDA path (through the C-ABI of libmsplit.so) against the CPU oracle on the
+same deterministic inputs.  Bars: bit-exact for CSR assembly, splitting and SpMV (same fma chain);
+fp64 reductions within 1e-12 relative (summation order differs); synchronous drivers within +-1 outer
+iteration and 1e-8 relative on the solution (BASELINE.json north_star)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def S():
+    from medane_tchakorom_ufc_thesis_repository_b200 import solver
+    from medane_tchakorom_ufc_thesis_repository_b200 import _lib
+    _lib.lib()
+    assert _lib.lib().msp_device_count() >= 1, "no CUDA device: these tests must run on the GPU box"
+    return solver
+
+
+# ------------------------------------------------------------------ assembly: bit-exact
+@pytest.mark.parametrize("m,n,G", [(2, 2, 2), (8, 8, 2), (12, 10, 3), (64, 48, 4), (512, 512, 2), (1, 7, 1), (7, 1, 1)])
+def test_poisson2d_bit_exact(S, oracle, m, n, G):
+    for k in range(G):
+        rp, ci, va = S.poisson2DMatrix(m, n, k, G)
+        orp, oci, ova = oracle.poisson2d(m, n, k, G)
+        assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(va, ova)
+
+
+def test_poisson2d_complete_and_square_rule(S, oracle):
+    rp, ci, va = S.poisson2DMatrix_complete(96, 96)
+    orp, oci, ova = oracle.poisson2d_complete(96, 96)
+    assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(va, ova)
+    with pytest.raises(S.MsplitError):
+        S.poisson2DMatrix_complete(8, 9)  # utils.c:390 assumes a square mesh
+
+
+@pytest.mark.parametrize("nx,ny,nz,G", [(2, 2, 2, 2), (6, 5, 4, 2), (16, 16, 16, 4), (64, 64, 64, 8)])
+def test_poisson3d_bit_exact(S, oracle, nx, ny, nz, G):
+    for k in range(G):
+        rp, ci, va = S.poisson3DMatrix(nx, ny, nz, k, G)
+        orp, oci, ova = oracle.poisson3d(nx, ny, nz, k, G)
+        assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(va, ova)
+
+
+def test_unity_known_answers_on_gpu(S):
+    # utils_test.c:172-221 rows of the 2x2 mesh, straight from the device assembly
+    rp, ci, va = S.poisson2DMatrix(2, 2, 0, 2)
+    assert list(ci) == [0, 1, 2, 0, 1, 3] and list(va) == [4, -1, -1, -1, 4, -1]
+    rp, ci, va = S.poisson2DMatrix(2, 2, 1, 2)
+    assert list(ci) == [0, 2, 3, 1, 2, 3] and list(va) == [-1, 4, -1, -1, -1, 4]
+    # utils_test.c:225-228: computeFinalResidualNorm == 2.54567588 with each block's own copy of x
+    tot = 0.0
+    data = [((0.1234, 0.5678, 0.9101, 0.1121), (0.3141, 0.5926)), ((0.8765, 0.4321, 0.5432, 0.6789), (0.2468, 0.1357))]
+    for k, (x, b) in enumerate(data):
+        e = S.Engine(2, 2, block=k, nblocks=2)
+        e.b = np.array(b)
+        e.x = np.array(x[2 * k:2 * k + 2])
+        other = np.array(x[2 * (1 - k):2 * (1 - k) + 2])
+        e.set_halo(1 - k, other)  # block 0's neighbour is above (side 1), block 1's below (side 0)
+        tot += e.block_residual_norm() ** 2
+        e.close()
+    assert abs(np.sqrt(tot) - 2.5456758807829405) < 1e-14
+
+
+@pytest.mark.parametrize("dim,shape,G,K", [(2, (24, 16), 3, 1), (2, (64, 64), 2, 0), (3, (8, 6, 9), 3, 2)])
+def test_split_bit_exact(S, oracle, dim, shape, G, K):
+    if dim == 2:
+        m, n = shape; p = 1
+        strip = oracle.poisson2d(m, n, K, G)
+    else:
+        m, n, p = shape
+        strip = oracle.poisson3d(m, n, p, K, G)
+    e = S.Engine(m, n, p, block=K, nblocks=G, keep_csr=True)
+    nb = e.nb
+    d = e.divideSubDomainIntoBlockMatrices(S.MAT_DIAG)
+    od = oracle.submatrix(*strip, K * nb, (K + 1) * nb)
+    for a, b in zip(d, od):
+        assert np.array_equal(a, b)
+    s_ = e.divideSubDomainIntoBlockMatrices(S.MAT_STRIP)
+    for a, b in zip(s_, strip):
+        assert np.array_equal(a, b)
+    off = e.divideSubDomainIntoBlockMatrices(S.MAT_OFFDIAG)
+    assert off[0][-1] + d[0][-1] == strip[0][-1]
+    # b_K = A_K,: * 1 (utils.c:626)
+    assert np.array_equal(e.b, oracle.spmv(*strip, np.ones(m * n * p)))
+    e.close()
+
+
+# ------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("dim,shape,G,K", [(2, (40, 33), 2, 1), (2, (128, 96), 4, 2), (3, (10, 9, 8), 2, 0), (3, (12, 12, 12), 3, 1)])
+def test_spmv_bit_exact(S, oracle, dim, shape, G, K):
+    rng = np.random.default_rng(123)
+    if dim == 2:
+        m, n = shape; p = 1
+        strip = oracle.poisson2d(m, n, K, G)
+    else:
+        m, n, p = shape
+        strip = oracle.poisson3d(m, n, p, K, G)
+    e = S.Engine(m, n, p, block=K, nblocks=G)
+    nb, H, ntot = e.nb, e.H, m * n * p
+    xg = rng.standard_normal(ntot)
+    off = K * nb
+    lo = xg[off - H:off] if K > 0 else None
+    hi = xg[off + nb:off + nb + H] if K < G - 1 else None
+    y = e.spmv(S.MAT_STRIP, xg[off:off + nb], lo, hi)
+    assert np.array_equal(y, oracle.spmv(*strip, xg))
+    diag = oracle.submatrix(*strip, off, off + nb)
+    y = e.spmv(S.MAT_DIAG, xg[off:off + nb])
+    assert np.array_equal(y, oracle.spmv(*diag, xg[off:off + nb]))
+    e.close()
+
+
+@pytest.mark.parametrize("nv", [1, 2, 7, 8, 9, 17, 30])
+def test_mdot_maxpy(S, nv):
+    rng = np.random.default_rng(nv)
+    e = S.Engine(37, 29, max_restart=30)  # odd row count: exercises the scalar tails
+    nb = e.nb
+    V = rng.standard_normal((nv, nb)); w = rng.standard_normal(nb)
+    h = e.mdot(V, w)
+    ref = V @ w
+    assert np.allclose(h, ref, rtol=1e-12, atol=1e-12)
+    w2, nrm = e.maxpy(V, -h, w)
+    refw = w.copy()
+    for j in range(nv):
+        refw = refw + (-h[j]) * V[j]
+    assert np.allclose(w2, refw, rtol=1e-12, atol=1e-12)
+    assert abs(nrm - np.linalg.norm(w2)) <= 1e-12 * max(1.0, nrm)
+    e.close()
+
+
+def test_update_rhs_and_residuals(S, oracle):
+    rng = np.random.default_rng(5)
+    m, n, G, K = 30, 20, 3, 1
+    strip = oracle.poisson2d(m, n, K, G)
+    e = S.Engine(m, n, block=K, nblocks=G)
+    nb, H = e.nb, e.H
+    xg = rng.standard_normal(m * n)
+    off = K * nb
+    e.x = xg[off:off + nb]
+    e.set_halo(0, xg[off - H:off]); e.set_halo(1, xg[off + nb:off + nb + H])
+    e.updateLocalRHS()
+    b = oracle.spmv(*strip, np.ones(m * n))
+    diag = oracle.submatrix(*strip, off, off + nb)
+    xoff = xg.copy(); xoff[off:off + nb] = 0.0
+    rhs_ref = b - oracle.spmv(*strip, xoff)
+    assert np.array_equal(e.rhs, rhs_ref)
+    assert abs(e.local_residual_norm() - np.linalg.norm(oracle.residual(*diag, rhs_ref, xg[off:off + nb]))) < 1e-12
+    assert abs(e.block_residual_norm() - oracle.block_residual_norm(*strip, b, xg)) < 1e-12
+    e.close()
+
+
+# ------------------------------------------------------------------ GMRES (inner_solver / gmres_solution)
+@pytest.mark.parametrize("N,restart,max_it,rtol,refine", [(32, 30, 1000, 1e-8, 0), (48, 10, 200, 1e-6, 0), (32, 30, 7, 1e-30, 0),
+                                                            (40, 20, 500, 1e-9, 2), (40, 20, 500, 1e-9, 1)])
+def test_standalone_gmres_matches_oracle(S, oracle, N, restart, max_it, rtol, refine):
+    e = S.Engine(N, N, max_restart=restart)
+    o = S.ksp_opts(restart=restart, max_it=max_it, rtol=rtol, abstol=1e-100, initial_rtol=1, cgs_refine=refine)
+    r = e.gmres_solve(o)
+    rp, ci, va = oracle.poisson2d_complete(N, N)
+    b = oracle.spmv(rp, ci, va, np.ones(N * N))
+    x, its, reason, rnorm = oracle.gmres(rp, ci, va, b, restart=restart, max_it=max_it, rtol=rtol, abstol=1e-100,
+                                         initial_rtol=1, cgs_refine=refine)
+    assert abs(r["gmres_its"] - its) <= 1
+    assert r["gmres_reason"] == reason
+    if r["gmres_its"] == its:
+        assert abs(r["gmres_rnorm"] - rnorm) <= 1e-8 * rnorm + 1e-300
+        assert np.linalg.norm(e.x - x) <= 1e-8 * np.linalg.norm(x)
+    e.close()
+
+
+def test_inner_solver_semantics(S, oracle):
+    # nonzero initial guess + UIR norm (utils.c:956-957); exact solution on entry => 0 its, CONVERGED_ATOL
+    e = S.Engine(16, 16)
+    e.x = np.ones(e.nb)
+    its, reason, rn = e.inner_solver(S.ksp_opts(max_it=20, rtol=1e-10))
+    assert its == 0 and reason == 3
+    e.x = np.zeros(e.nb)
+    its, reason, rn = e.inner_solver(S.ksp_opts(restart=30, max_it=5, rtol=1e-10, abstol=1e-100))
+    rp, ci, va = oracle.poisson2d_complete(16, 16)
+    b = oracle.spmv(rp, ci, va, np.ones(256))
+    x, oits, oreason, orn = oracle.gmres(rp, ci, va, b, restart=30, max_it=5, rtol=1e-10, abstol=1e-100, initial_rtol=1, guess_nonzero=1)
+    assert (its, reason) == (oits, oreason) == (5, -3)
+    assert np.linalg.norm(e.x - x) <= 1e-12 * np.linalg.norm(x)
+    with pytest.raises(S.MsplitError):
+        e.inner_solver(S.ksp_opts(restart=31))  # exceeds the engine's Krylov storage
+    e.close()
+
+
+# ------------------------------------------------------------------ minimisation pieces
+def test_tsqr_minimisation_matches_lstsq(S, oracle):
+    rng = np.random.default_rng(11)
+    m, n, G, s = 24, 16, 2, 5
+    factors, blocks = [], []
+    Sg = rng.standard_normal((s, m * n))
+    for K in range(G):
+        e = S.Engine(m, n, block=K, nblocks=G, s=s)
+        nb, H = e.nb, e.H
+        off = K * nb
+        for t in range(s):
+            e.x = Sg[t, off:off + nb]
+            if K > 0: e.set_halo(0, Sg[t, off - H:off])
+            if K < G - 1: e.set_halo(1, Sg[t, off + nb:off + nb + H])
+            e.push_iterate(t)
+        e.spmm_AS("SMSM_GLOBAL")
+        factors.append(e.minimize_local_qr("SMSM_GLOBAL"))
+        blocks.append(e)
+    alpha, rn = S.tsqr_combine(s, factors)
+    # reference: R = A S over the whole grid, exact least squares
+    A = oracle.poisson2d(m, n, 0, 1)
+    R = np.stack([oracle.spmv(*A, Sg[t]) for t in range(s)], axis=1)
+    b = oracle.spmv(*A, np.ones(m * n))
+    a_ref, rn_ref = oracle.lstsq_qr(R, b)
+    assert np.allclose(alpha, a_ref, rtol=1e-9, atol=1e-11)
+    assert abs(rn - rn_ref) <= 1e-10 * rn_ref
+    for K, e in enumerate(blocks):
+        e.apply_alpha("SMSM_GLOBAL", alpha)
+        nb = e.nb
+        assert np.allclose(e.x, (Sg.T @ alpha)[K * nb:(K + 1) * nb], rtol=1e-12, atol=1e-12)
+        e.close()
+
+
+# ------------------------------------------------------------------ whole drivers, all blocks in one process on one GPU
+def _golden_runs():
+    with open(os.path.join(GOLD, "oracle_sync_runs.json")) as f:
+        return json.load(f)["runs"]
+
+
+@pytest.mark.parametrize("g", _golden_runs(), ids=lambda g: f"{g['alg']}-{g['m']}x{g['n']}x{g.get('p', 1)}-G{g['nblocks']}")
+def test_sync_driver_parity(S, oracle, g):
+    grp = S.Group(g["m"], g["n"], g.get("p", 1), nblocks=g["nblocks"], s=g["s"], max_restart=g["inner"]["restart"])
+    inner = S.ksp_opts(**g["inner"])
+    res = grp.solve(g["alg"], s=g["s"], rtol=g["rtol"], inner=inner, max_outer=3000)
+    ref = oracle.solve(g["alg"], g["m"], g["n"], p=g.get("p", 1), nblocks=g["nblocks"], s=g["s"], rtol=g["rtol"],
+                       inner=g["inner"], max_outer=3000)
+    its = res[0]["outer_its"]
+    assert all(r["outer_its"] == its for r in res)
+    assert abs(its - g["outer_its"]) <= 1, (its, g["outer_its"])
+    assert abs(res[0]["norm0"] - g["norm0"]) <= 1e-13 * g["norm0"]
+    if its == ref["outer_its"]:
+        x = grp.solution()
+        assert np.linalg.norm(x - ref["x"]) <= 1e-8 * np.linalg.norm(ref["x"])
+        assert abs(res[0]["final_residual"] - ref["final_residual"]) <= 1e-6 * ref["final_residual"] + 1e-14
+    # size-independent property: the reported residual is the true residual of the returned x
+    if g["alg"] in ("SM", "SMSM_GLOBAL"):
+        assert res[0]["final_residual"] <= g["rtol"] * res[0]["norm0"] * 1.0000001
+    grp.close()
+
+
+def test_config1_msm_512(S, oracle):
+    """BASELINE config 1: MSM, 2-D 512x512, 2 blocks, rtol 1e-6, inner GMRES(30) max_it 50 rtol 1e-10 UIR
+    (running_bulk_test_local:96-101).  Oracle golden: tests/golden/config1_msm_512.json."""
+    with open(os.path.join(GOLD, "config1_msm_512.json")) as f:
+        gold = json.load(f)
+    grp = S.Group(512, 512, nblocks=2, max_restart=30)
+    res = grp.solve("SM", rtol=1e-6, inner=S.ksp_opts(restart=30, max_it=50, rtol=1e-10, abstol=1e-100), max_outer=20000)
+    assert abs(res[0]["outer_its"] - gold["outer_its"]) <= 1
+    assert res[0]["final_residual"] <= 1e-6 * res[0]["norm0"] * 1.0000001
+    x = grp.solution()
+    xg = np.load(os.path.join(GOLD, "config1_msm_512_x_sample.npy"))
+    idx = np.array(gold["sample_idx"])
+    if res[0]["outer_its"] == gold["outer_its"]:
+        assert np.linalg.norm(x[idx] - xg) <= 1e-8 * np.linalg.norm(xg)
+    grp.close()
+
+
+def test_errors(S):
+    with pytest.raises(S.MsplitError):
+        S.Engine(10, 10, nblocks=3)  # grid lines not divisible by the block count
+    with pytest.raises(S.MsplitError):
+        S.Engine(8, 8, max_restart=100)
+    g = S.Group(16, 16, nblocks=2, s=2)
+    with pytest.raises(S.MsplitError):
+        g.solve("SMSM_GLOBAL", s=5)  # s exceeds basis storage
+    g.close()

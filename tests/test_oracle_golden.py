@@ -1,0 +1,188 @@
+"""Pins the CPU oracle against every known answer the reference's own unit tests hold for this path
+(src/tests/utils_test.c, run there as `mpirun -n 4 ./bin/utils_test`: 2 blocks x 2 ranks)."""
+import json
+import os
+
+import numpy as np
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def dense_rows(rp, ci, va, ncols):
+    n = len(rp) - 1
+    D = np.zeros((n, ncols))
+    for r in range(n):
+        for k in range(rp[r], rp[r + 1]):
+            D[r, ci[k]] = va[k]
+    return D
+
+
+def test_computeDimensionRelatedVariables(oracle):
+    # utils_test.c:38-64 — 2x2 mesh, 4 ranks, npb = 2
+    exp = {0: (0, 0), 1: (1, 0), 2: (0, 1), 3: (1, 1)}
+    for rank in range(4):
+        d = oracle.dimension_related(4, 2, rank, 2, 2)
+        assert d["njacobi_blocks"] == 2 and d["n_mesh_points"] == 4 and d["jacobi_block_size"] == 2
+        assert (d["proc_local_rank"], d["rank_jacobi_block"]) == exp[rank]
+
+
+def test_poisson2DMatrix(oracle):
+    # utils_test.c:172-221
+    D0 = dense_rows(*oracle.poisson2d(2, 2, 0, 2), 4)
+    D1 = dense_rows(*oracle.poisson2d(2, 2, 1, 2), 4)
+    assert np.array_equal(D0, [[4, -1, -1, 0], [-1, 4, 0, -1]])
+    assert np.array_equal(D1, [[-1, 0, 4, -1], [0, -1, -1, 4]])
+
+
+def test_poisson3DMatrix(oracle):
+    # utils_test.c:66-170 — 2x2x2 mesh: diag 6, -1 at +-1, +-2, +-4 where in range
+    D = np.vstack([dense_rows(*oracle.poisson3d(2, 2, 2, k, 2), 8) for k in range(2)])
+    exp = np.zeros((8, 8))
+    for r in range(8):
+        i, j, k = r % 2, (r // 2) % 2, r // 4
+        exp[r, r] = 6
+        if i > 0: exp[r, r - 1] = -1
+        if i < 1: exp[r, r + 1] = -1
+        if j > 0: exp[r, r - 2] = -1
+        if j < 1: exp[r, r + 2] = -1
+        if k > 0: exp[r, r - 4] = -1
+        if k < 1: exp[r, r + 4] = -1
+    assert np.array_equal(D, exp)
+    with open(os.path.join(GOLD, "utils_test_poisson3d_2x2x2.json")) as f:
+        gold = json.load(f)
+    assert np.array_equal(D, np.array(gold["rows"]))
+
+
+def test_computeFinalResidualNorm(oracle):
+    # utils_test.c:225-228 with inputs :285-316 => 2.54567588 (TEST_ASSERT_EQUAL_FLOAT)
+    x0 = np.array([0.1234, 0.5678, 0.9101, 0.1121]); b0 = np.array([0.3141, 0.5926])
+    x1 = np.array([0.8765, 0.4321, 0.5432, 0.6789]); b1 = np.array([0.2468, 0.1357])
+    n0 = oracle.block_residual_norm(*oracle.poisson2d(2, 2, 0, 2), b0, x0)
+    n1 = oracle.block_residual_norm(*oracle.poisson2d(2, 2, 1, 2), b1, x1)
+    got = np.sqrt(n0 * n0 + n1 * n1)
+    assert abs(np.float32(got) - np.float32(2.54567588)) <= 1e-5 * 2.54567588
+    assert abs(got - 2.5456758807829405) < 1e-14
+
+
+def test_csr_sorted_and_counts(oracle):
+    # nnz_total = 5mn - 2m - 2n (2-D), 7N^3 - 6N^2 (3-D)  
+    for (m, n, G) in [(8, 8, 2), (6, 10, 3), (16, 4, 4)]:
+        tot = 0
+        for k in range(G):
+            rp, ci, va = oracle.poisson2d(m, n, k, G)
+            tot += rp[-1]
+            for r in range(len(rp) - 1):
+                row = ci[rp[r]:rp[r + 1]]
+                assert np.all(np.diff(row) > 0)
+        assert tot == 5 * m * n - 2 * m - 2 * n
+    N = 6
+    tot = sum(oracle.poisson3d(N, N, N, k, 2)[0][-1] for k in range(2))
+    assert tot == 7 * N ** 3 - 6 * N ** 2
+
+
+def test_split_matches_scipy(oracle):
+    import scipy.sparse as sp
+    m, n, G, K = 8, 6, 2, 1
+    rp, ci, va = oracle.poisson2d(m, n, K, G)
+    nb = m * n // G
+    A = sp.csr_matrix((va, ci, rp), shape=(nb, m * n))
+    drp, dci, dva = oracle.submatrix(rp, ci, va, K * nb, (K + 1) * nb)
+    D = sp.csr_matrix((dva, dci, drp), shape=(nb, nb))
+    assert (abs(D - A[:, K * nb:(K + 1) * nb]).sum()) == 0
+
+
+def test_gmres_matches_scipy_solution(oracle):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    n = 24
+    rp, ci, va = oracle.poisson2d_complete(n, n)
+    A = sp.csr_matrix((va, ci, rp), shape=(n * n, n * n))
+    b = A @ np.ones(n * n)
+    x, its, reason, rnorm = oracle.gmres(rp, ci, va, b, restart=30, rtol=1e-10, max_it=2000, initial_rtol=1)
+    assert reason == 2
+    assert np.linalg.norm(b - A @ x) <= 1.5e-10 * np.linalg.norm(b)
+    assert abs(rnorm - np.linalg.norm(b - A @ x)) <= 1e-6 * rnorm + 1e-14
+    xs = spla.spsolve(A.tocsc(), b)
+    assert np.linalg.norm(x - xs) < 1e-7
+
+
+def test_gmres_max_it_cuts_cycle_and_min_it_rule(oracle):
+    n = 16
+    rp, ci, va = oracle.poisson2d_complete(n, n)
+    b = oracle.spmv(rp, ci, va, np.ones(n * n))
+    # max_it = 7 < restart: exactly 7 iterations, DIVERGED_ITS (-3), iterate still updated
+    x, its, reason, _ = oracle.gmres(rp, ci, va, b, restart=30, rtol=1e-30, max_it=7)
+    assert its == 7 and reason == -3 and np.linalg.norm(x) > 0
+    # starting from the exact solution: residual 0 on entry => CONVERGED_ATOL, 0 iterations
+    x, its, reason, _ = oracle.gmres(rp, ci, va, b, x0=np.ones(n * n), restart=30, guess_nonzero=1)
+    assert its == 0 and reason == 3
+
+
+def test_lsqr_and_qr_agree(oracle):
+    rng = np.random.default_rng(7)
+    R = rng.standard_normal((200, 5))
+    b = rng.standard_normal(200)
+    a_ref, *_ = np.linalg.lstsq(R, b, rcond=None)
+    a_qr, rn_qr = oracle.lstsq_qr(R, b)
+    a_ls, its, reason, rn_ls = oracle.lsqr(R, b, max_it=70, rtol=1e-15)
+    assert np.allclose(a_qr, a_ref, rtol=1e-10, atol=1e-12)
+    assert np.allclose(a_ls, a_ref, rtol=1e-8, atol=1e-10)
+    assert abs(rn_qr - np.linalg.norm(b - R @ a_ref)) < 1e-10
+    assert abs(rn_ls - rn_qr) < 1e-8
+    assert its == 70  # inconsistent system + rtol 1e-15: LSQR always runs max_it
+
+
+def test_sync_drivers_converge(oracle):
+    inner = dict(restart=30, max_it=20, rtol=1e-10, abstol=1e-100)
+    r = oracle.solve("SM", 32, 32, nblocks=2, rtol=1e-6, inner=dict(restart=30, max_it=50, rtol=1e-10, abstol=1e-100))
+    assert r["rc"] == 0 and r["final_residual"] <= 1e-6 * r["norm0"] and r["outer_its"] == 108
+    r = oracle.solve("SMSM_GLOBAL", 32, 32, nblocks=2, s=5, rtol=1e-6, inner=inner)
+    assert r["rc"] == 0 and r["outer_its"] == 6 and r["final_residual"] <= 1e-6 * r["norm0"]
+    rl = oracle.solve("SMSM_GLOBAL", 32, 32, nblocks=2, s=5, rtol=1e-6, inner=inner, outer_type="lsqr", outer_max_it=70)
+    assert abs(rl["outer_its"] - r["outer_its"]) <= 1
+    for alg in ("SMSM_SEMI_LOCAL", "SMSM_LOCAL"):
+        r = oracle.solve(alg, 32, 32, nblocks=2, s=5, rtol=1e-6, inner=inner)
+        assert r["rc"] == 0 and r["outer_its"] > 0 and r["last_norm"] <= 1e-6 / np.sqrt(2) * r["norm0"]
+    with open(os.path.join(GOLD, "oracle_sync_runs.json")) as f:
+        gold = json.load(f)
+    for g in gold["runs"]:
+        r = oracle.solve(g["alg"], g["m"], g["n"], p=g.get("p", 1), nblocks=g["nblocks"], s=g["s"], rtol=g["rtol"],
+                         inner=g["inner"])
+        assert r["outer_its"] == g["outer_its"], g
+        assert abs(r["final_residual"] - g["final_residual"]) <= 1e-6 * g["final_residual"]
+
+
+def test_conv_detection_two_blocks(oracle):
+    # both roots under the threshold with fresh data every step => elected leader = max rank, positive verdict
+    cd = oracle.ConvDetect(2)
+    it = [0, 0]
+    finished = False
+    for step in range(40):
+        for k in (0, 1):
+            other = 1 - k
+            cd.data_arrival(k, other, cd.phase_tag(other), it[other])
+            cd.step(k, True)
+            it[k] += 1
+        if cd.state(0) == cd.FINISHED and cd.state(1) == cd.FINISHED:
+            finished = True
+            break
+    assert finished
+    # never under the threshold => stays NORMAL
+    cd = oracle.ConvDetect(2)
+    for step in range(20):
+        for k in (0, 1):
+            cd.data_arrival(k, 1 - k, 0, step)
+            cd.step(k, False)
+    assert cd.state(0) == cd.NORMAL and cd.state(1) == cd.NORMAL
+
+
+def test_async_drivers_reach_residual(oracle):
+    # inexact inner solves (max_it 3): the local residual then tracks the global one and the detection
+    # protocol (pseudo-periods, election, verification, verdict) stops near the requested tolerance
+    inner = dict(restart=30, max_it=3, rtol=1e-10, abstol=1e-100)
+    r = oracle.solve("AM", 24, 24, nblocks=2, rtol=1e-5, inner=inner, periods=[1, 2], max_outer=4000)
+    assert r["rc"] == 0 and r["final_residual"] <= 2e-5 * r["norm0"]
+    assert r["outer_its_block"][0] == 2 * r["outer_its_block"][1]  # block 1 runs every second tick
+    for alg in ("AMAM_GLOBAL", "AMAM_SEMI_LOCAL", "AMAM_LOCAL"):
+        r = oracle.solve(alg, 24, 24, nblocks=2, s=4, rtol=1e-5, inner=inner, periods=[1, 2], max_outer=4000)
+        assert r["rc"] == 0 and r["final_residual"] <= 1e-4 * r["norm0"], alg
