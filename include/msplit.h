@@ -82,6 +82,7 @@ typedef struct {
   msp_ksp_opts inner;   /* -inner{K}_ksp_* */
   int max_outer;        /* safety cap (reference: none); 0 = 1000000 */
   int record_history;
+  int profile;          /* bracket every hot-kernel launch with CUDA events and fill the per-class t_, b_ and n_ fields */
   /* async emulation in one process: block K runs a step at tick t iff t % period[K] == 0 */
   int period[MSP_MAX_BLOCKS];
 } msp_solve_opts;
@@ -101,6 +102,8 @@ typedef struct {
   int64_t kernel_launches;    /* kernels launched by this engine inside the timed region */
   /* per-kernel-class device time inside the timed region (ms) and launches, when profiling is on */
   double t_spmv_ms, t_mdot_ms, t_maxpy_ms, t_other_ms;
+  double b_spmv, b_mdot, b_maxpy, b_other;   /* algorithmic bytes moved by each class (SURVEY.md §8d formulas) */
+  int64_t n_spmv, n_mdot, n_maxpy, n_other;  /* launches per class */
 } msp_result;
 
 int msp_version(void);

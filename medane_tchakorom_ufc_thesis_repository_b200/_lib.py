@@ -38,7 +38,7 @@ class Problem(C.Structure):
 class SolveOpts(C.Structure):
     _fields_ = [
         ("alg", C.c_int), ("s", C.c_int), ("rtol", C.c_double), ("inner", KspOpts), ("max_outer", C.c_int),
-        ("record_history", C.c_int), ("period", C.c_int * MAX_BLOCKS),
+        ("record_history", C.c_int), ("profile", C.c_int), ("period", C.c_int * MAX_BLOCKS),
     ]
 
 
@@ -49,6 +49,8 @@ class Result(C.Structure):
         ("gmres_its", C.c_int), ("gmres_reason", C.c_int), ("gmres_rnorm", C.c_double),
         ("hist_len", C.c_int), ("hist", C.c_double * 4096), ("kernel_launches", C.c_int64),
         ("t_spmv_ms", C.c_double), ("t_mdot_ms", C.c_double), ("t_maxpy_ms", C.c_double), ("t_other_ms", C.c_double),
+        ("b_spmv", C.c_double), ("b_mdot", C.c_double), ("b_maxpy", C.c_double), ("b_other", C.c_double),
+        ("n_spmv", C.c_int64), ("n_mdot", C.c_int64), ("n_maxpy", C.c_int64), ("n_other", C.c_int64),
     ]
 
     def as_dict(self):
@@ -58,6 +60,8 @@ class Result(C.Structure):
             "elapsed_s": self.elapsed_s, "gmres_its": self.gmres_its, "gmres_reason": self.gmres_reason,
             "gmres_rnorm": self.gmres_rnorm, "hist": np.array(self.hist[: self.hist_len]),
             "kernel_launches": self.kernel_launches,
+            "prof": {c: {"ms": getattr(self, f"t_{c}_ms"), "bytes": getattr(self, f"b_{c}"), "launches": getattr(self, f"n_{c}")}
+                     for c in ("spmv", "mdot", "maxpy", "other")},
         }
 
 

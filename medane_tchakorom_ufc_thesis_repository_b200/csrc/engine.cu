@@ -192,6 +192,37 @@ struct msp_engine {
   bool own_comm = false;
   CdState *cd = nullptr;
   int64_t launches = 0;
+  // per-class profiling (CUDA events around each hot-kernel launch, on the launching stream)
+  bool prof = false;
+  struct ProfRec { int cls; cudaEvent_t a, b; double bytes; };
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t get_event() {
+    if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void prof_begin(int cls, double bytes) {
+    if (!prof) return;
+    ProfRec r{cls, get_event(), get_event(), bytes};
+    cudaEventRecord(r.a, st);
+    recs.push_back(r);
+  }
+  void prof_end() { if (prof) cudaEventRecord(recs.back().b, st); }
+  void prof_collect(msp_result *res) {
+    if (!prof) return;
+    cudaStreamSynchronize(st);
+    double t[4] = {0, 0, 0, 0}, by[4] = {0, 0, 0, 0}; int64_t n[4] = {0, 0, 0, 0};
+    for (auto &r : recs) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.a, r.b);
+      t[r.cls] += ms; by[r.cls] += r.bytes; n[r.cls]++;
+      ev_pool.push_back(r.a); ev_pool.push_back(r.b);
+    }
+    recs.clear();
+    res->t_spmv_ms = t[0]; res->t_mdot_ms = t[1]; res->t_maxpy_ms = t[2]; res->t_other_ms = t[3];
+    res->b_spmv = by[0]; res->b_mdot = by[1]; res->b_maxpy = by[2]; res->b_other = by[3];
+    res->n_spmv = n[0]; res->n_mdot = n[1]; res->n_maxpy = n[2]; res->n_other = n[3];
+  }
   double local_sig = 0; // sticky convergence signal
   // deterministic turn taking for the emulated asynchronous schedule
   struct msp_group *grp = nullptr;
@@ -259,9 +290,11 @@ static int set_device(int device) {
 template <int MODE, bool RESID, bool SCALE, bool NORM>
 static void launch_spmv_w(msp_engine *e, const SpmvArgs &a, int ws_slot, GmresCtl *ctl_rw) {
   const int g = grid_for(((long long)a.nb + 1) / 2, 8);
+  e->prof_begin(0, 12.0 * (double)e->nnz + 4.0 * (e->nb + 1) + 16.0 * e->nb + (SCALE ? 8.0 * e->nb : 0.0) + (RESID ? 8.0 * e->nb : 0.0));
   if (a.W == 5) k_spmv_ell<5, MODE, RESID, SCALE, NORM><<<g, MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
   else if (a.W == 7) k_spmv_ell<7, MODE, RESID, SCALE, NORM><<<g, MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
   else k_spmv_ell<0, MODE, RESID, SCALE, NORM><<<g, MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
+  e->prof_end();
   e->launches++;
 }
 
@@ -282,7 +315,9 @@ static void launch_mdot(msp_engine *e, int nv, const double *V, long long ldv, c
   ngroups = (nv + a.per_group - 1) / a.per_group;
   int per_sm = std::max(1, 8 / ngroups);
   dim3 grid(grid_for((long long)e->nb / 4, per_sm), ngroups);
+  e->prof_begin(1, 8.0 * e->nb * (nv + 1));
   k_mdot<<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws);
+  e->prof_end();
   e->launches++;
 }
 
@@ -292,7 +327,9 @@ static void launch_maxpy(msp_engine *e, int nv, const double *V, long long ldv, 
   MaxpyArgs a{};
   a.nb = e->nb; a.nv = nv; a.ld = ldv; a.V = V; a.coef = coef; a.w = w; a.norm_out = norm_out; a.ctl = e->ctl;
   a.guard_it = guard_it; a.guard_refine = guard_refine; a.pass = pass; a.last_pass = 1;
+  e->prof_begin(2, 8.0 * e->nb * (nv + 2));
   k_maxpy_norm<FIN><<<grid_for((long long)e->nb / 2, 8), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot);
+  e->prof_end();
   e->launches++;
 }
 
@@ -697,8 +734,10 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
   if (alg != MSP_ALG_SM && (s < 1 || s > e->smax)) MSP_FAIL("s exceeds the engine's basis storage");
   const int max_outer = o->max_outer > 0 ? o->max_outer : 1000000;
   memset(res, 0, sizeof(*res));
-  // global_norm_0 = computeFinalResidualNorm(x) before the loop (…multisplitting.c:162)
-  RC(op_resid_sumsq(e, true, 0));
+  // global_norm_0 = computeFinalResidualNorm(x = 0) before the loop (…multisplitting.c:162) = ||b||; computed from b so
+  // that a call continuing from a previous iterate keeps the same reference norm
+  k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->b, 0.0, e->ws, 2, e->dsc + 0);
+  e->launches++;
   RC(allreduce_host(e, 0, 1));
   res->norm0 = std::sqrt(e->hsc[0]);
   const double thr_global = std::max(atol, o->rtol * res->norm0);
@@ -708,6 +747,7 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   CK(cudaEventRecord(ev0, e->st));
   const int64_t launches0 = e->launches;
+  e->prof = o->profile != 0;
   bool done = false;
   int sticky = 0;
   std::vector<double> uaug((size_t)(s + 1) * (s + 1)), alpha(std::max(s, 1));
@@ -804,6 +844,8 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
   res->elapsed_s = ms * 1e-3;
   res->kernel_launches = e->launches - launches0;
   CK(cudaEventDestroy(ev0)); CK(cudaEventDestroy(ev1));
+  e->prof_collect(res);
+  e->prof = false;
   // closing exchange + true residual + error (comm_sync_send_and_receive_final comm.c:199, utils.c:575, :1045)
   RC(op_publish_boundary(e));
   RC(exchange_sync(e));

@@ -221,8 +221,8 @@ class Engine:
     def comm_connect(self, side: int, handle: bytes):
         check(_lib.lib().msp_comm_connect(self.h, side, handle))
 
-    def solve(self, alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_outer=0, record_history=True):
-        o = make_solve_opts(alg, s, rtol, inner, max_outer, record_history)
+    def solve(self, alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_outer=0, record_history=True, profile=False):
+        o = make_solve_opts(alg, s, rtol, inner, max_outer, record_history, profile=profile)
         res = Result()
         check(_lib.lib().msp_solve(self.h, C.byref(o), C.byref(res)))
         return res.as_dict()
@@ -244,7 +244,7 @@ def comm_unique_id() -> bytes:
 
 
 def make_solve_opts(alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_outer=0, record_history=True,
-                    periods: Optional[Sequence[int]] = None) -> SolveOpts:
+                    periods: Optional[Sequence[int]] = None, profile=False) -> SolveOpts:
     o = SolveOpts()
     o.alg = ALG[alg] if isinstance(alg, str) else int(alg)
     o.s = s
@@ -252,6 +252,7 @@ def make_solve_opts(alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_ou
     o.inner = inner if inner is not None else ksp_opts()
     o.max_outer = max_outer
     o.record_history = int(record_history)
+    o.profile = int(profile)
     for i in range(_lib.MAX_BLOCKS):
         o.period[i] = periods[i] if periods and i < len(periods) else 0
     return o
@@ -284,8 +285,9 @@ class Group:
         except Exception:
             pass
 
-    def solve(self, alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_outer=0, record_history=True, periods=None):
-        o = make_solve_opts(alg, s, rtol, inner, max_outer, record_history, periods)
+    def solve(self, alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_outer=0, record_history=True, periods=None,
+              profile=False):
+        o = make_solve_opts(alg, s, rtol, inner, max_outer, record_history, periods, profile)
         res = (Result * self.nblocks)()
         check(_lib.lib().msp_group_solve(self.h, C.byref(o), res))
         return [r.as_dict() for r in res]

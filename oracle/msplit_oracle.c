@@ -12,11 +12,13 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
 
 #define API __attribute__((visibility("default")))
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 #define CHUNK 4096 /* fixed reduction chunk: results independent of the OpenMP thread count */
 
 /* ======================================================================= */
@@ -818,7 +820,9 @@ static int solve_gmres_standalone(const orc_config *c, orc_result *res, double *
   orc_ksp_opts o = c->inner;
   o.guess_nonzero = 0;
   res->norm0 = orc_norm2(n, b);
+  double t0 = now_s();
   orc_gmres((int)n, rp, ci, va, b, x, &o, &res->gmres_its, &res->gmres_reason, &res->gmres_rnorm, res->hist, 4096);
+  res->elapsed_s = now_s() - t0;
   res->last_norm = res->gmres_rnorm;
   res->outer_its = res->gmres_its;
   res->final_residual = orc_block_residual_norm((int)n, rp, ci, va, b, x);
@@ -856,6 +860,7 @@ API int orc_solve(const orc_config *c, orc_result *res, double *x_out) {
   double *bglob = NULL, *xmin = NULL;
   int sig[16] = {0};
   int rc = 0;
+  const double t_start = now_s();
 
   if (!is_async) {
     if (minim == 1 || minim == 2) {
@@ -1067,6 +1072,7 @@ API int orc_solve(const orc_config *c, orc_result *res, double *x_out) {
     orc_cd_destroy(cd);
   }
 
+  res->elapsed_s = now_s() - t_start;
   /* closing synchronous exchange + true residual + error (e.g. …-global.c:376-388) */
   exchange_all(B, G);
   res->final_residual = global_resid(B, G);

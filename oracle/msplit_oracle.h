@@ -107,6 +107,7 @@ typedef struct {
   int gmres_its;            /* alg GMRES: KSP its */
   int gmres_reason;
   double gmres_rnorm;
+  double elapsed_s;         /* wall-clock of the outer loop only (the reference's MPI_Wtime region) */
 } orc_result;
 
 /* ---- assembly (bit-exact gate) ---- */

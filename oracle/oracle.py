@@ -54,7 +54,7 @@ class Result(C.Structure):
         ("outer_its", C.c_int), ("outer_its_block", C.c_int * 16), ("inner_its_total", C.c_int64),
         ("norm0", C.c_double), ("last_norm", C.c_double), ("final_residual", C.c_double),
         ("error", C.c_double), ("hist_len", C.c_int), ("hist", C.c_double * 4096),
-        ("gmres_its", C.c_int), ("gmres_reason", C.c_int), ("gmres_rnorm", C.c_double),
+        ("gmres_its", C.c_int), ("gmres_reason", C.c_int), ("gmres_rnorm", C.c_double), ("elapsed_s", C.c_double),
     ]
 
 
@@ -255,6 +255,7 @@ def solve(alg, m, n, p=1, nblocks=2, s=4, rtol=1e-6, inner=None, outer_type="qr"
         "final_residual": res.final_residual, "error": res.error,
         "hist": np.array(res.hist[: res.hist_len]),
         "gmres_its": res.gmres_its, "gmres_reason": res.gmres_reason, "gmres_rnorm": res.gmres_rnorm, "x": x,
+        "elapsed_s": res.elapsed_s,
     }
     return out
 
