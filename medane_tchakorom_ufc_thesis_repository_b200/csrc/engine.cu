@@ -597,6 +597,13 @@ static int op_push_iterate(msp_engine *e, int t) {
 static bool kind_is_local(int kind) { return kind == MSP_ALG_SMSM_LOCAL || kind == MSP_ALG_AMAM_LOCAL; }
 
 static int op_spmm(msp_engine *e, int kind, int s) {
+  // basis of successive corrections (same span as the iterates, far better conditioned)
+  k_diff_basis<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, s, e->ld, e->S);
+  e->launches++;
+  if (!kind_is_local(kind)) {
+    if (e->has_nb[0]) { k_diff_basis<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->H, s, e->H, e->Slo); e->launches++; }
+    if (e->has_nb[1]) { k_diff_basis<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->H, s, e->H, e->Shi); e->launches++; }
+  }
   SpmmArgs a{};
   a.nb = e->nb; a.W = e->W; a.H = e->H; a.s = s; a.ld = e->ld; a.lds = e->ld; a.ecol = e->ecol; a.eval = e->eval;
   a.S = e->S; a.R = e->R;

@@ -704,6 +704,18 @@ __global__ void k_lincomb(int nb, int s, long long lds, const double *__restrict
     x[r] = t;
   }
 }
+// basis change of the minimisation: [x^1 .. x^s] -> [x^1, x^2-x^1, .., x^s-x^(s-1)] in place (same span, much better
+// conditioned least-squares problem).  One pass, each thread owns a row.
+__global__ void k_diff_basis(long long rows, int s, long long lds, double *__restrict__ S) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    double prev = S[r];
+    for (int t = 1; t < s; t++) {
+      const double cur = S[(long long)t * lds + r];
+      S[(long long)t * lds + r] = cur - prev;
+      prev = cur;
+    }
+  }
+}
 // sum of (x - 1)^2 and generic sum of squares through the norm slot
 __global__ void __launch_bounds__(MSPK_THREADS) k_sumsq(long long n, const double *__restrict__ x, double shift, ReduceWs ws, int ws_slot, double *out) {
   double acc = 0.0;

@@ -802,6 +802,21 @@ static int ls_solve(const orc_config *c, int64_t nrows, int s, const double *R, 
   return orc_lstsq_qr(nrows, s, R, ld, b, alpha, rnorm);
 }
 
+/* Exact-LS path only (not the reference's LSQR path): replace the basis [x^1 .. x^s] by [x^1, x^2-x^1, .., x^s-x^(s-1)].
+ * Same span, hence the same minimiser in exact arithmetic, but the successive corrections are far less collinear than
+ * the iterates themselves, which removes most of the cancellation from alpha and from x = S alpha. */
+static void diff_basis(double *S, int64_t rows, int s, int64_t ld) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < rows; i++) {
+    double prev = S[i];
+    for (int t = 1; t < s; t++) {
+      double cur = S[(size_t)t * ld + i];
+      S[(size_t)t * ld + i] = cur - prev;
+      prev = cur;
+    }
+  }
+}
+
 static void push_hist(orc_result *res, double v) {
   if (res->hist_len < 4096) res->hist[res->hist_len++] = v;
 }
@@ -895,6 +910,10 @@ API int orc_solve(const orc_config *c, orc_result *res, double *x_out) {
         exchange_all(B, G);
         if (minim == 3) for (int K = 0; K < G; K++) memcpy(S + ((size_t)K * s + t) * nb, B[K].view + B[K].off, sizeof(double) * nb);
         else memcpy(S + (size_t)t * ntot, B[0].view, sizeof(double) * ntot); /* all views agree after a synchronous exchange */
+      }
+      if (c->outer.type == ORC_OUTER_QR) {
+        if (minim == 3) for (int K = 0; K < G; K++) diff_basis(S + (size_t)K * s * nb, nb, s, nb);
+        else diff_basis(S, ntot, s, ntot);
       }
       if (minim == 1) {
         /* …-global.c:325-354: R = A S (block rows), complete R everywhere, LS on (R, b), x = S alpha */
@@ -1020,6 +1039,7 @@ API int orc_solve(const orc_config *c, orc_result *res, double *x_out) {
           else if (minim) memcpy(SS[K] + (size_t)t * ntot, Bk->view, sizeof(double) * ntot);
           inner_outer[K]++;
         }
+        if (minim && c->outer.type == ORC_OUTER_QR) diff_basis(SS[K], (minim == 3) ? nb : ntot, s, (minim == 3) ? nb : ntot);
         double ln;
         if (minim == 0) {
           ln = local_resid(Bk);
