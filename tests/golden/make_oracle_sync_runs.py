@@ -10,7 +10,15 @@ from oracle import oracle as O  # noqa: E402
 
 inner20 = dict(restart=30, max_it=20, rtol=1e-10, abstol=1e-100)
 inner50 = dict(restart=30, max_it=50, rtol=1e-10, abstol=1e-100)
+inner5 = dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)
 cases = [
+    # tight-parity regime (inexact inner solves: iterates well separated)
+    dict(alg="SMSM_GLOBAL", m=32, n=32, nblocks=2, s=5, rtol=1e-6, inner=inner5),
+    dict(alg="SMSM_GLOBAL", m=64, n=48, nblocks=4, s=4, rtol=1e-6, inner=inner5),
+    dict(alg="SMSM_SEMI_LOCAL", m=32, n=32, nblocks=2, s=5, rtol=1e-5, inner=inner5),
+    dict(alg="SMSM_LOCAL", m=32, n=32, nblocks=4, s=3, rtol=1e-5, inner=inner5),
+    dict(alg="SMSM_GLOBAL", m=16, n=16, p=16, nblocks=4, s=5, rtol=1e-6, inner=inner5),
+    dict(alg="SMSM_LOCAL", m=12, n=10, p=8, nblocks=2, s=4, rtol=1e-5, inner=inner5),
     dict(alg="SM", m=32, n=32, nblocks=2, s=0, rtol=1e-6, inner=inner50),
     dict(alg="SM", m=48, n=32, nblocks=4, s=0, rtol=1e-5, inner=inner20),
     dict(alg="SMSM_GLOBAL", m=32, n=32, nblocks=2, s=5, rtol=1e-6, inner=inner20),

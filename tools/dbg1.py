@@ -3,7 +3,8 @@ sys.path.insert(0, "/root/repo")
 import numpy as np
 from medane_tchakorom_ufc_thesis_repository_b200 import solver as S
 from oracle import oracle as O
-inner = dict(restart=30, max_it=20, rtol=1e-10, abstol=1e-100)
+import sys as _s
+inner = dict(restart=30, max_it=20, rtol=1e-10, abstol=1e-100, cgs_refine=int(_s.argv[1]) if len(_s.argv)>1 else 0)
 for mo in (1,2,3,6):
     grp = S.Group(32, 32, nblocks=2, s=5, max_restart=30)
     res = grp.solve("SMSM_GLOBAL", s=5, rtol=1e-6, inner=S.ksp_opts(**inner), max_outer=mo)

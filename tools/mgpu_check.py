@@ -1,0 +1,44 @@
+"""Run under torchrun (one rank per GPU): the per-process path (NCCL allreduce + CUDA-IPC P2P boundary stores)
+against the CPU oracle.  Prints 'MGPU OK' on rank 0."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from medane_tchakorom_ufc_thesis_repository_b200 import distributed as D  # noqa: E402
+from medane_tchakorom_ufc_thesis_repository_b200 import solver as S  # noqa: E402
+
+rank, world, local = D.env_rank()
+torch.cuda.set_device(local)
+cases = [
+    ("SM", 64, 64, 1, 0, 1e-6, dict(restart=30, max_it=20, rtol=1e-10, abstol=1e-100)),
+    ("SMSM_GLOBAL", 64, 64, 1, 5, 1e-6, dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)),
+    ("SMSM_SEMI_LOCAL", 64, 64, 1, 4, 1e-5, dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)),
+    ("SMSM_LOCAL", 64, 64, 1, 4, 1e-5, dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)),
+    ("SMSM_GLOBAL", 16, 16, 16, 5, 1e-6, dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)),
+]
+ok = True
+for alg, m, n, p, s, rtol, inner in cases:
+    eng = D.make_distributed_engine(m, n, p, s=max(s, 0), max_restart=30)
+    res = eng.solve(alg, s=s, rtol=rtol, inner=S.ksp_opts(**inner), max_outer=5000)
+    x_local = eng.x
+    parts = D.allgather_bytes(x_local.tobytes())
+    if rank == 0:
+        from oracle import oracle as O
+        ref = O.solve(alg, m, n, p=p, nblocks=world, s=s, rtol=rtol, inner=inner, max_outer=5000)
+        x = np.concatenate([np.frombuffer(b, dtype=np.float64) for b in parts])
+        dx = np.linalg.norm(x - ref["x"]) / np.linalg.norm(ref["x"])
+        good = abs(res["outer_its"] - ref["outer_its"]) <= 1 and (res["outer_its"] != ref["outer_its"] or dx <= 1e-8)
+        ok &= good
+        print(f"{alg} {m}x{n}x{p} G={world}: its {res['outer_its']} (oracle {ref['outer_its']}), dx {dx:.2e}, "
+              f"resid {res['final_residual'] / res['norm0']:.3e}, elapsed {res['elapsed_s'] * 1e3:.1f} ms {'ok' if good else 'FAIL'}", flush=True)
+    eng.close()
+    D.barrier()
+if rank == 0:
+    print("MGPU OK" if ok else "MGPU FAIL", flush=True)
+import torch.distributed as dist
+if dist.is_initialized():
+    dist.destroy_process_group()
+sys.exit(0 if ok else 1)
