@@ -255,7 +255,7 @@ def test_sync_driver_parity(S, oracle, g):
         tight = g["alg"] == "SM" or g["nblocks"] == 1 or g["inner"]["max_it"] <= 5
         xtol = 1e-8 if tight else 100 * g["rtol"]
         assert np.linalg.norm(x - ref["x"]) <= xtol * np.linalg.norm(ref["x"])
-        assert abs(res[0]["final_residual"] - ref["final_residual"]) <= (1e-6 if tight else 0.2) * ref["final_residual"] + 1e-14
+        assert abs(res[0]["final_residual"] - ref["final_residual"]) <= (1e-3 if tight else 0.2) * ref["final_residual"] + 1e-14
     # size-independent property: the reported residual is the true residual of the returned x
     if g["alg"] in ("SM", "SMSM_GLOBAL"):
         assert res[0]["final_residual"] <= g["rtol"] * res[0]["norm0"] * 1.0000001
