@@ -182,6 +182,8 @@ int msp_comm_unique_id(void *id128);                                  /* ncclGet
 int msp_comm_init(msp_engine *e, const void *id128, int rank, int nranks); /* ncclCommInitRank */
 int msp_comm_export(msp_engine *e, void *handle64);                   /* cudaIpcGetMemHandle of the receive window */
 int msp_comm_connect(msp_engine *e, int side, const void *handle64);  /* cudaIpcOpenMemHandle of neighbour side */
+int msp_comm_connect_block(msp_engine *e, int block, const void *handle64); /* any block: the async global minimisation
+                                                                               publishes its TSQR factor to every block */
 int msp_solve(msp_engine *e, const msp_solve_opts *o, msp_result *res); /* the drivers' do { } while loops */
 
 /* async convergence detection, one step of this block's state machine on the device

@@ -74,7 +74,7 @@ EXPORTS = [
     "msp_local_residual_norm", "msp_block_residual_norm", "msp_error_norm_sq", "msp_push_iterate", "msp_spmm_AS",
     "msp_minimize_local_qr", "msp_apply_alpha", "msp_tsqr_combine", "msp_op_spmv", "msp_op_mdot", "msp_op_maxpy",
     "msp_bench_kernel", "msp_gmres_solve", "msp_group_create", "msp_group_destroy", "msp_group_engine",
-    "msp_group_solve", "msp_comm_unique_id", "msp_comm_init", "msp_comm_export", "msp_comm_connect", "msp_solve",
+    "msp_group_solve", "msp_comm_unique_id", "msp_comm_init", "msp_comm_export", "msp_comm_connect", "msp_comm_connect_block", "msp_solve",
     "msp_conv_detect_step",
 ]
 
@@ -138,6 +138,7 @@ def lib() -> C.CDLL:
     L.msp_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
     L.msp_comm_export.argtypes = [vp, C.c_char_p]
     L.msp_comm_connect.argtypes = [vp, C.c_int, C.c_char_p]
+    L.msp_comm_connect_block.argtypes = [vp, C.c_int, C.c_char_p]
     L.msp_solve.argtypes = [vp, C.POINTER(SolveOpts), C.POINTER(Result)]
     L.msp_conv_detect_step.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L

@@ -151,18 +151,24 @@ struct NcclComm : Comm {
 // ------------------------------------------------------------------------------------------------
 // engine
 // ------------------------------------------------------------------------------------------------
-struct AsyncHdr { int seq, tag, iter, pad; };
-// receive window, one allocation (exportable with one cudaIpcMemHandle):
-//   [ lo par0 | lo par1 | hi par0 | hi par1 ] H doubles each, then 2 AsyncHdr (lo, hi), then the CdMailbox
+// receive window, one allocation (exportable with one cudaIpcMemHandle), in doubles:
+//   [ lo par0 | lo par1 | hi par0 | hi par1 ]  4 x H   boundary layers (sync: parity = exchange count; async: seq & 1)
+//   [ 8 ]                                      two AsyncHdrDev (lo, hi)
+//   [ 16 ]                                     CdMailbox (convergence-detection messages)
+//   [ G x fslot ]                              TSQR factor mailboxes of the asynchronous global minimisation:
+//                                              slot J = { seq, (s+1)^2 factor of block J, seq }
 struct Window {
   double *base = nullptr;
   size_t bytes = 0;
-  int H = 0;
+  int H = 0, G = 0, fslot = 0;
   double *halo(int side, int par) const { return base + (size_t)(side * 2 + par) * H; }
-  AsyncHdr *hdr(int side) const { return reinterpret_cast<AsyncHdr *>(base + (size_t)4 * H) + side; }
-  CdMailbox *mailbox() const { return reinterpret_cast<CdMailbox *>(reinterpret_cast<char *>(base + (size_t)4 * H) + 64); }
-  static size_t size_for(int H) { return sizeof(double) * 4 * (size_t)H + 64 + sizeof(CdMailbox) + 64; }
+  AsyncHdrDev *hdr(int side) const { return reinterpret_cast<AsyncHdrDev *>(base + (size_t)4 * H) + side; }
+  CdMailbox *mailbox() const { return reinterpret_cast<CdMailbox *>(base + (size_t)4 * H + 8); }
+  double *factor(int J) const { return base + (size_t)4 * H + 8 + 16 + (size_t)J * fslot; }
+  static int fslot_for(int smax) { return (smax + 1) * (smax + 1) + 2; }
+  static size_t size_for(int H, int G, int smax) { return sizeof(double) * ((size_t)4 * H + 8 + 16 + (size_t)G * fslot_for(smax) + 8); }
 };
+static_assert(sizeof(CdMailbox) == 128, "mailbox layout");
 
 struct msp_engine {
   int device = 0;
@@ -187,6 +193,14 @@ struct msp_engine {
   Window win;            // own receive window
   Window peer[2];        // neighbours' windows (peer / IPC mapped); base null if no neighbour
   bool peer_ipc[2] = {false, false};
+  Window peer_any[MSP_MAX_BLOCKS]; // every block's window (factor mailboxes of the async global minimisation)
+  bool peer_any_ipc[MSP_MAX_BLOCKS] = {};
+  int *aint = nullptr;   // device ints: [0..1] last seen async header seq per side
+  ProbeDecision *dec = nullptr; // [2]
+  int async_sent[2] = {0, 0};
+  int factor_sent = 0;
+  std::vector<double> fcache; // newest valid factor seen from each block [G x fslot]
+  std::vector<int> fcache_seq;
   int par = 0;
   Comm *comm = nullptr;
   bool own_comm = false;
@@ -340,10 +354,10 @@ static int engine_free(msp_engine *e) {
   if (!e) return 0;
   cudaSetDevice(e->device);
   if (e->st) cudaStreamSynchronize(e->st);
-  for (int s = 0; s < 2; s++)
-    if (e->peer[s].base && e->peer_ipc[s]) cudaIpcCloseMemHandle(e->peer[s].base);
+  for (int J = 0; J < MSP_MAX_BLOCKS; J++)
+    if (e->peer_any[J].base && e->peer_any_ipc[J]) cudaIpcCloseMemHandle(e->peer_any[J].base);
   void *ptrs[] = {e->rp, e->ci, e->va, e->ecol, e->eval, e->brow, e->b, e->rhs, e->x, e->halo[0], e->halo[1], e->V, e->Wb[0],
-                  e->Wb[1], e->S, e->Slo, e->Shi, e->R, e->ctl, e->ws.partial, e->ws.counter, e->dsc, e->win.base, e->cd};
+                  e->Wb[1], e->S, e->Slo, e->Shi, e->R, e->ctl, e->ws.partial, e->ws.counter, e->dsc, e->win.base, e->cd, e->aint, e->dec};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (e->hsc) cudaFreeHost(e->hsc);
   if (e->own_comm && e->comm) delete e->comm;
@@ -427,8 +441,15 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   }
   dalloc(&e->ws.partial, sizeof(double) * (size_t)MSPK_MAX_PART * 8 * 24);
   dalloc(&e->dsc, sizeof(double) * 256);
-  e->win.H = e->H; e->win.bytes = Window::size_for(e->H);
+  e->win.H = e->H; e->win.G = p->nblocks; e->win.fslot = Window::fslot_for(e->smax);
+  e->win.bytes = Window::size_for(e->H, p->nblocks, e->smax);
   dalloc(&e->win.base, e->win.bytes);
+  if (ok && cudaMalloc(&e->aint, sizeof(int) * 16) != cudaSuccess) ok = false;
+  if (ok) cudaMemsetAsync(e->aint, 0, sizeof(int) * 16, e->st);
+  if (ok && cudaMalloc(&e->dec, sizeof(ProbeDecision) * 2) != cudaSuccess) ok = false;
+  if (ok) cudaMemsetAsync(e->dec, 0, sizeof(ProbeDecision) * 2, e->st);
+  e->fcache.assign((size_t)p->nblocks * e->win.fslot, 0.0);
+  e->fcache_seq.assign(p->nblocks, 0);
   if (ok && cudaMalloc(&e->ws.counter, sizeof(unsigned) * 64) != cudaSuccess) ok = false;
   if (ok) cudaMemsetAsync(e->ws.counter, 0, sizeof(unsigned) * 64, e->st);
   if (ok && cudaMalloc(&e->ctl, sizeof(GmresCtl)) != cudaSuccess) ok = false;
@@ -928,6 +949,20 @@ static int group_wire(msp_group *g) {
       }
       e->peer[side] = p->win; e->peer_ipc[side] = false;
     }
+    for (int J = 0; J < g->G; J++) {
+      if (J == k) continue;
+      msp_engine *p = g->eng[J];
+      if (p->device != e->device) {
+        cudaSetDevice(e->device);
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, e->device, p->device);
+        if (!can) MSP_FAIL("peer access between the two GPUs is not available");
+        cudaError_t er = cudaDeviceEnablePeerAccess(p->device, 0);
+        if (er != cudaSuccess && er != cudaErrorPeerAccessAlreadyEnabled) MSP_FAIL("cudaDeviceEnablePeerAccess failed");
+        cudaGetLastError();
+      }
+      e->peer_any[J] = p->win; e->peer_any_ipc[J] = false;
+    }
   }
   return 0;
 }
@@ -1261,6 +1296,7 @@ int msp_group_destroy(msp_group *g) {
 msp_engine *msp_group_engine(msp_group *g, int k) { return (g && k >= 0 && k < g->G) ? g->eng[k] : nullptr; }
 
 int engine_solve_async_group(msp_group *g, const msp_solve_opts *o, msp_result *res);
+static int engine_solve_async(msp_engine *e, const msp_solve_opts *o, msp_result *res);
 
 int msp_group_solve(msp_group *g, const msp_solve_opts *o, msp_result *res) {
   if (!g || !o || !res) MSP_FAIL("null argument");
@@ -1314,24 +1350,38 @@ int msp_comm_export(msp_engine *e, void *handle64) {
   memcpy(handle64, &h, 64);
   return 0;
 }
+static int connect_block(msp_engine *e, int J, const void *handle64) {
+  if (J < 0 || J >= e->prob.nblocks || J == e->prob.block) MSP_FAIL("bad block index");
+  cudaSetDevice(e->device);
+  if (!e->peer_any[J].base) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    e->peer_any[J] = e->win; // same geometry on every block
+    e->peer_any[J].base = (double *)p;
+    e->peer_any_ipc[J] = true;
+  }
+  if (J == e->prob.block - 1) e->peer[0] = e->peer_any[J];
+  if (J == e->prob.block + 1) e->peer[1] = e->peer_any[J];
+  return 0;
+}
 int msp_comm_connect(msp_engine *e, int side, const void *handle64) {
   if (!e || !handle64 || side < 0 || side > 1) MSP_FAIL("bad argument");
   if (!e->has_nb[side]) MSP_FAIL("no neighbour on that side");
-  cudaSetDevice(e->device);
-  cudaIpcMemHandle_t h;
-  memcpy(&h, handle64, 64);
-  void *p = nullptr;
-  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-  e->peer[side].base = (double *)p; e->peer[side].H = e->H; e->peer[side].bytes = e->win.bytes; e->peer_ipc[side] = true;
-  return 0;
+  return connect_block(e, side == 0 ? e->prob.block - 1 : e->prob.block + 1, handle64);
+}
+int msp_comm_connect_block(msp_engine *e, int block, const void *handle64) {
+  if (!e || !handle64) MSP_FAIL("bad argument");
+  return connect_block(e, block, handle64);
 }
 int msp_solve(msp_engine *e, const msp_solve_opts *o, msp_result *res) {
   if (!e || !o || !res) MSP_FAIL("null argument");
   cudaSetDevice(e->device);
   if (o->alg == MSP_ALG_GMRES) return engine_gmres(e, &o->inner, res);
-  if (o->alg >= MSP_ALG_AM) MSP_FAIL("asynchronous variants: not available through msp_solve yet");
   for (int side = 0; side < 2; side++)
     if (e->has_nb[side] && !e->peer[side].base) MSP_FAIL("neighbour window not connected (msp_comm_connect)");
+  if (o->alg >= MSP_ALG_AM) return engine_solve_async(e, o, res);
   return engine_solve_sync(e, o, res);
 }
 
@@ -1350,7 +1400,228 @@ int msp_conv_detect_step(msp_engine *e, int under_threshold, int *state, int *ph
 
 } // extern "C"
 
-int engine_solve_async_group(msp_group *, const msp_solve_opts *, msp_result *) {
-  g_err = "asynchronous variants are not built yet";
-  return 1;
+// ------------------------------------------------------------------------------------------------
+// asynchronous variants (…multisplitting_prime.c:321-393, …-minimization-{global,semi-local,local}_prime.c)
+// ------------------------------------------------------------------------------------------------
+struct AsyncRun {
+  int iters = 0;         // number_of_iterations
+  int inner_outer = 0;   // number_of_inner_times_outer_iterations
+  int state = 0;
+  double thr_local = 0;
+  double last_norm = 0;
+  std::vector<double> uaug, alpha, all;
+};
+
+static int slot_of_side(const msp_engine *e, int side) { return e->has_nb[0] ? side : 0; }
+
+// comm_async_probe_and_receive_prime comm.c:455-529 for both neighbours
+static int async_probe(msp_engine *e) {
+  for (int side = 0; side < 2; side++) {
+    if (!e->has_nb[side]) continue;
+    k_async_probe<<<1, 32, 0, e->st>>>(e->win.hdr(side), e->cd, slot_of_side(e, side), e->aint + side, e->dec + side);
+    k_async_copy<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->dec + side, e->H, e->win.halo(side, 0), e->win.halo(side, 1), e->halo[side]);
+    e->launches += 2;
+  }
+  return 0;
+}
+// comm_async_test_and_send_prime comm.c:531-554: P2P store of the boundary layers + header release
+static int async_publish(msp_engine *e, int iter) {
+  for (int side = 0; side < 2; side++) {
+    if (!e->peer[side].base) continue;
+    const int q = ++e->async_sent[side];
+    // my first layer goes to the lower neighbour's "hi" window, my last layer to the upper neighbour's "lo" window
+    double *dst = e->peer[side].halo(1 - side, q & 1);
+    k_publish_boundary<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->nb, e->H, e->x, side == 0 ? dst : nullptr, side == 1 ? dst : nullptr);
+    k_async_release<<<1, 32, 0, e->st>>>(e->peer[side].hdr(1 - side), e->cd, iter, q);
+    e->launches += 2;
+  }
+  return 0;
+}
+
+static int async_begin(msp_engine *e, const msp_solve_opts *o, msp_result *res, AsyncRun *run) {
+  const int G = e->prob.nblocks, s = o->s;
+  memset(res, 0, sizeof(*res));
+  if (o->alg != MSP_ALG_AM && (s < 1 || s > e->smax)) MSP_FAIL("s exceeds the engine's basis storage");
+  for (int side = 0; side < 2; side++)
+    if (e->has_nb[side] && !e->peer[side].base) MSP_FAIL("neighbour window not connected");
+  k_cd_init<<<1, 32, 0, e->st>>>(e->cd, e->prob.block, G, e->win.mailbox(), e->peer[0].base ? e->peer[0].mailbox() : nullptr,
+                                 e->peer[1].base ? e->peer[1].mailbox() : nullptr, e->win.hdr(0), e->win.hdr(1), e->aint);
+  k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->b, 0.0, e->ws, 2, e->dsc + 0);
+  e->launches += 2;
+  RC(allreduce_host(e, 0, 1));
+  res->norm0 = std::sqrt(e->hsc[0]);
+  run->thr_local = std::max(1e-100, (o->rtol / std::sqrt((double)G)) * 1.0 * res->norm0);
+  run->uaug.assign((size_t)(s + 1) * (s + 1), 0.0);
+  run->alpha.assign(std::max(s, 1), 0.0);
+  std::fill(e->fcache_seq.begin(), e->fcache_seq.end(), 0);
+  RC(op_update_rhs(e)); // …multisplitting_prime.c:315
+  return 0;
+}
+
+// one pass of the do { } while (state != FINISHED) body of this block
+static int async_step(msp_engine *e, const msp_solve_opts *o, msp_result *res, AsyncRun *run) {
+  const int alg = o->alg, s = o->s, G = e->prob.nblocks;
+  msp_ksp_opts in = o->inner;
+  in.initial_rtol = 1; in.guess_nonzero = 1;
+  int its = 0, reason = 0;
+  if (alg == MSP_ALG_AM) {
+    RC(async_probe(e));
+    RC(op_update_rhs(e));
+    RC(op_inner_solve(e, &in, false, &its, &reason, nullptr));
+    res->inner_its_total += its;
+    RC(async_publish(e, run->iters));
+    RC(op_resid_sumsq(e, false, 1));
+  } else {
+    for (int t = 0; t < s; t++) {
+      RC(async_probe(e));
+      RC(op_update_rhs(e));
+      RC(op_inner_solve(e, &in, false, &its, &reason, nullptr));
+      res->inner_its_total += its;
+      RC(async_publish(e, run->inner_outer));
+      RC(async_probe(e));
+      RC(op_push_iterate(e, t));
+      run->inner_outer++;
+    }
+    if (alg == MSP_ALG_AMAM_GLOBAL) {
+      RC(op_spmm(e, alg, s));
+      RC(op_local_qr(e, alg, s, run->uaug.data()));
+      const int nn = (s + 1) * (s + 1), fs = e->win.fslot;
+      // publish my TSQR factor to every block (replaces the R-slab Isend, comm.c:330-347), newest wins
+      if (G > 1) {
+        std::vector<double> slot(fs, 0.0);
+        const double q = (double)(++e->factor_sent);
+        slot[0] = q; slot[fs - 1] = q;
+        memcpy(slot.data() + 1, run->uaug.data(), sizeof(double) * nn);
+        for (int J = 0; J < G; J++)
+          if (J != e->prob.block && e->peer_any[J].base)
+            CK(cudaMemcpyAsync(e->peer_any[J].factor(e->prob.block), slot.data(), sizeof(double) * fs, cudaMemcpyHostToDevice, e->st));
+        CK(cudaStreamSynchronize(e->st));
+        // newest factors the others have published so far (comm_async_probe_and_receive_min comm.c:288-328)
+        std::vector<double> mine((size_t)G * fs);
+        CK(cudaMemcpyAsync(mine.data(), e->win.factor(0), sizeof(double) * (size_t)G * fs, cudaMemcpyDeviceToHost, e->st));
+        CK(cudaStreamSynchronize(e->st));
+        for (int J = 0; J < G; J++) {
+          if (J == e->prob.block) continue;
+          const double *sl = mine.data() + (size_t)J * fs;
+          if (sl[0] > 0 && sl[0] == sl[fs - 1] && (int)sl[0] != e->fcache_seq[J]) {
+            memcpy(e->fcache.data() + (size_t)J * fs, sl, sizeof(double) * fs);
+            e->fcache_seq[J] = (int)sl[0];
+          }
+        }
+      }
+      run->all.clear();
+      int nfac = 0;
+      for (int J = 0; J < G; J++) {
+        const double *f = nullptr;
+        if (J == e->prob.block) f = run->uaug.data();
+        else if (e->fcache_seq[J] > 0) f = e->fcache.data() + (size_t)J * fs + 1;
+        if (f) { run->all.insert(run->all.end(), f, f + nn); nfac++; }
+      }
+      RC(tsqr_combine(s, nfac, run->all.data(), run->alpha.data(), nullptr));
+      RC(op_apply_alpha(e, alg, s, run->alpha.data()));
+      RC(op_resid_sumsq(e, true, 1)); // ||b_K - A_K,: x_min|| (…-global_prime.c:436-437)
+    } else if (alg == MSP_ALG_AMAM_SEMI_LOCAL) {
+      RC(op_spmm(e, alg, s));
+      RC(op_local_qr(e, alg, s, run->uaug.data()));
+      RC(tsqr_combine(s, 1, run->uaug.data(), run->alpha.data(), nullptr));
+      RC(op_apply_alpha(e, alg, s, run->alpha.data()));
+      RC(op_resid_sumsq(e, true, 1));
+    } else {
+      RC(op_spmm(e, alg, s));
+      RC(op_update_rhs(e));
+      RC(op_local_qr(e, alg, s, run->uaug.data()));
+      RC(tsqr_combine(s, 1, run->uaug.data(), run->alpha.data(), nullptr));
+      RC(op_apply_alpha(e, alg, s, run->alpha.data()));
+      RC(op_resid_sumsq(e, false, 1));
+    }
+  }
+  // root of the block: UnderThreshold + convergence detection state machine on the device
+  k_cd_step<<<1, 32, 0, e->st>>>(e->cd, 0, e->dsc + 1, run->thr_local);
+  e->launches++;
+  CK(cudaMemcpyAsync(e->hsc + 48, e->cd, 8, cudaMemcpyDeviceToHost, e->st));
+  RC(read_scalars(e, 1, 1));
+  int hs[2];
+  memcpy(hs, e->hsc + 48, 8);
+  run->state = hs[0];
+  run->last_norm = std::sqrt(e->hsc[1]);
+  run->iters++;
+  res->last_norm = run->last_norm;
+  if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = run->last_norm;
+  return 0;
+}
+
+static int async_finish(msp_engine *e, msp_result *res, AsyncRun *run) {
+  res->outer_its = run->iters;
+  // closing synchronous exchange + true residual + error (…multisplitting_prime.c:404-420)
+  RC(op_publish_boundary(e));
+  RC(exchange_sync(e));
+  RC(op_resid_sumsq(e, true, 0));
+  k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->x, 1.0, e->ws, 2, e->dsc + 1);
+  e->launches++;
+  RC(allreduce_host(e, 0, 2));
+  res->final_residual = std::sqrt(e->hsc[0]);
+  res->error = std::sqrt(e->hsc[1]);
+  return 0;
+}
+
+// free-running: what each process (or each block thread) executes
+static int engine_solve_async(msp_engine *e, const msp_solve_opts *o, msp_result *res) {
+  AsyncRun run;
+  RC(async_begin(e, o, res, &run));
+  RC(e->comm->barrier(e->st));
+  const int max_outer = o->max_outer > 0 ? o->max_outer : 1000000;
+  const int64_t l0 = e->launches;
+  auto t0 = std::chrono::steady_clock::now();
+  while (run.state != 3 && run.iters < max_outer) RC(async_step(e, o, res, &run));
+  CK(cudaStreamSynchronize(e->st));
+  res->elapsed_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  res->kernel_launches = e->launches - l0;
+  RC(e->comm->barrier(e->st));
+  return async_finish(e, res, &run);
+}
+
+int engine_solve_async_group(msp_group *g, const msp_solve_opts *o, msp_result *res) {
+  const int G = g->G;
+  bool scheduled = false;
+  for (int k = 0; k < G; k++) scheduled |= (o->period[k] > 0);
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> errs(G);
+  if (!scheduled) {
+    std::vector<std::thread> th;
+    for (int k = 0; k < G; k++)
+      th.emplace_back([&, k] {
+        cudaSetDevice(g->eng[k]->device);
+        rcs[k] = engine_solve_async(g->eng[k], o, &res[k]);
+        if (rcs[k]) errs[k] = g_err;
+      });
+    for (auto &t : th) t.join();
+    for (int k = 0; k < G; k++) if (rcs[k]) { g_err = errs[k]; return rcs[k]; }
+    return 0;
+  }
+  // deterministic schedule (tests): block K runs one step at tick t iff t % period[K] == 0, blocks in index order;
+  // collective phases (norm0, closing exchange) still need one thread per block
+  std::vector<AsyncRun> runs(G);
+  auto par_all = [&](auto fn) {
+    std::vector<std::thread> th;
+    for (int k = 0; k < G; k++)
+      th.emplace_back([&, k] { cudaSetDevice(g->eng[k]->device); rcs[k] = fn(k); if (rcs[k]) errs[k] = g_err; });
+    for (auto &t : th) t.join();
+    for (int k = 0; k < G; k++) if (rcs[k]) { g_err = errs[k]; return rcs[k]; }
+    return 0;
+  };
+  RC(par_all([&](int k) { int rc = async_begin(g->eng[k], o, &res[k], &runs[k]); if (!rc) rc = g->eng[k]->comm->barrier(g->eng[k]->st); return rc; }));
+  const long long max_ticks = (long long)(o->max_outer > 0 ? o->max_outer : 1000000) * 64;
+  int nfin = 0;
+  for (long long tick = 0; nfin < G && tick < max_ticks; tick++) {
+    for (int k = 0; k < G; k++) {
+      const int per = o->period[k] > 0 ? o->period[k] : 1;
+      if (tick % per || runs[k].state == 3) continue;
+      cudaSetDevice(g->eng[k]->device);
+      RC(async_step(g->eng[k], o, &res[k], &runs[k]));
+      CK(cudaStreamSynchronize(g->eng[k]->st));
+      if (runs[k].state == 3) nfin++;
+    }
+  }
+  if (nfin < G) MSP_FAIL("asynchronous schedule cap reached before every block finished");
+  return par_all([&](int k) { return async_finish(g->eng[k], &res[k], &runs[k]); });
 }

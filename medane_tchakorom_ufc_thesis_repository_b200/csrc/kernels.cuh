@@ -776,22 +776,31 @@ struct CdState {
   int my_slot_at[2];
 };
 
+// seqlock cell: seq odd = being written.  Writer: seq = 2q+1, payload, seq = 2q+2.  Reader: consume when seq is even,
+// new, and unchanged after the payload has been read (otherwise the message is picked up at the next step, which is
+// what a later MPI_Iprobe would do in the reference).
 __device__ inline void cd_send(CdState *s, int nslot, int type, int a, int b) {
   CdMailbox *mb = s->outbox[nslot];
   if (!mb) return;
   CdMsg *m = &mb->m[s->my_slot_at[nslot]][type];
-  m->a = a; m->b = b;
-  __threadfence_system();
   const int q = ++s->sent[nslot][type];
-  *reinterpret_cast<volatile int *>(&m->seq) = q;
+  *reinterpret_cast<volatile int *>(&m->seq) = 2 * q - 1;
+  __threadfence_system();
+  *reinterpret_cast<volatile int *>(&m->a) = a;
+  *reinterpret_cast<volatile int *>(&m->b) = b;
+  __threadfence_system();
+  *reinterpret_cast<volatile int *>(&m->seq) = 2 * q;
   __threadfence_system();
 }
 __device__ inline bool cd_recv(CdState *s, int nslot, int type, int *a, int *b) {
   volatile CdMsg *m = &s->inbox->m[nslot][type];
   const int q = m->seq;
-  if (q == s->seen[nslot][type]) return false;
+  if ((q & 1) || q == s->seen[nslot][type]) return false;
   __threadfence_system();
-  *a = m->a; *b = m->b;
+  const int va = m->a, vb = m->b;
+  __threadfence_system();
+  if (m->seq != q) return false;
+  *a = va; *b = vb;
   s->seen[nslot][type] = q;
   return true;
 }
@@ -898,4 +907,62 @@ __global__ void k_cd_step(CdState *s, int under, const double *local_norm_sq, do
     for (int i = 0; i < NN; i++) if (i != sl) cd_send(s, i, 3, s->phase_tag, b);
   }
   s->state_seen = s->state;
+}
+
+// ------------------------------------------------------------------------------------------------
+// asynchronous boundary exchange (comm_async_test_and_send_prime / comm_async_probe_and_receive_prime,
+// comm.c:455-554): the payload (one boundary layer) is stored into the neighbour's double-buffered receive
+// window, then a header {seq, PhaseTag, iteration} is released.  The receiver takes the newest header it
+// sees ("drain the queue, keep the last message"), asks receive_data_dependency whether to accept it, and
+// copies the layer into its private halo.  A layer overwritten while it is being copied mixes two iterates
+// of the neighbour, which an asynchronous iteration tolerates by construction.
+// ------------------------------------------------------------------------------------------------
+struct AsyncHdrDev { int seq, tag, iter, pad; };
+struct ProbeDecision { int copy, buf, seq, pad; };
+
+__global__ void k_async_release(AsyncHdrDev *peer_hdr, const CdState *cd, int iter, int seq) {
+  if (threadIdx.x || blockIdx.x || !peer_hdr) return;
+  __threadfence_system();
+  *reinterpret_cast<volatile int *>(&peer_hdr->tag) = cd->phase_tag;
+  *reinterpret_cast<volatile int *>(&peer_hdr->iter) = iter;
+  __threadfence_system();
+  *reinterpret_cast<volatile int *>(&peer_hdr->seq) = seq;
+  __threadfence_system();
+}
+__global__ void k_async_probe(const AsyncHdrDev *hdr, CdState *cd, int nslot, int *seen_seq, ProbeDecision *dec) {
+  if (threadIdx.x || blockIdx.x) return;
+  const volatile AsyncHdrDev *h = hdr;
+  const int q = h->seq;
+  dec->copy = 0;
+  if (q == *seen_seq) return;
+  __threadfence_system();
+  const int tag = h->tag, iter = h->iter;
+  *seen_seq = q;
+  dec->buf = q & 1;
+  dec->seq = q;
+  dec->copy = cd_data_arrival(cd, nslot, tag, iter);
+}
+__global__ void k_async_copy(const ProbeDecision *dec, int H, const double *win0, const double *win1, double *halo) {
+  if (!dec->copy) return;
+  const volatile double *src = dec->buf ? win1 : win0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H; i += gridDim.x * blockDim.x) halo[i] = src[i];
+}
+__global__ void k_cd_init(CdState *s, int me, int nblocks, CdMailbox *inbox, CdMailbox *out_lo, CdMailbox *out_hi,
+                          const AsyncHdrDev *hdr_lo, const AsyncHdrDev *hdr_hi, int *seen_hdr) {
+  if (threadIdx.x || blockIdx.x) return;
+  // messages left over from a previous solve are not part of this one
+  for (int sl = 0; sl < 2; sl++)
+    for (int t = 0; t < 4; t++) s->seen[sl][t] = reinterpret_cast<volatile CdMsg *>(&inbox->m[sl][t])->seq;
+  seen_hdr[0] = reinterpret_cast<const volatile AsyncHdrDev *>(hdr_lo)->seq;
+  seen_hdr[1] = reinterpret_cast<const volatile AsyncHdrDev *>(hdr_hi)->seq;
+  // keep `seen`/`sent` counters across solves: the mailboxes persist
+  s->me = me;
+  s->nb_neighbors = 0;
+  s->outbox[0] = s->outbox[1] = nullptr;
+  if (me > 0) { s->neighbors[s->nb_neighbors] = me - 1; s->outbox[s->nb_neighbors] = out_lo; s->my_slot_at[s->nb_neighbors] = (me - 1 > 0) ? 1 : 0; s->nb_neighbors++; }
+  if (me < nblocks - 1) { s->neighbors[s->nb_neighbors] = me + 1; s->outbox[s->nb_neighbors] = out_hi; s->my_slot_at[s->nb_neighbors] = 0; s->nb_neighbors++; }
+  s->inbox = inbox;
+  for (int i = 0; i < 2; i++) { s->last_iter[i] = -1; s->responses[i] = 0; }
+  cd_init_state(s);
+  s->under = 0; s->phase_tag = 0; s->state_seen = 0; s->response_sent = 0;
 }

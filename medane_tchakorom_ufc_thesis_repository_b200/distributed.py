@@ -109,16 +109,22 @@ def barrier():
 
 
 def connect_blocks(rank: int, world: int, export_window: Callable[[], bytes], connect: Callable[[int, bytes], None],
-                   make_unique_id: Callable[[], bytes], comm_init: Callable[[bytes, int, int], None]) -> None:
+                   make_unique_id: Callable[[], bytes], comm_init: Callable[[bytes, int, int], None],
+                   connect_block: Optional[Callable[[int, bytes], None]] = None) -> None:
     """Bootstrap of the per-GPU engines: rank 0 creates the NCCL id, every rank joins the communicator,
     exports its receive window and maps the windows of blocks K-1 / K+1 (replaces the MPI communicators
     built at …multisplitting.c:66-77)."""
     uid = broadcast_bytes(make_unique_id() if rank == 0 else None, 0)
     comm_init(uid, rank, world)
     handles = allgather_bytes(export_window())
-    for side, nb in enumerate(neighbours(rank, world)):
-        if nb is not None:
-            connect(side, handles[nb])
+    if connect_block is not None:
+        for blk in range(world):
+            if blk != rank:
+                connect_block(blk, handles[blk])
+    else:
+        for side, nb in enumerate(neighbours(rank, world)):
+            if nb is not None:
+                connect(side, handles[nb])
     barrier()
 
 
@@ -129,5 +135,6 @@ def make_distributed_engine(m, n, p=1, s=0, max_restart=30, keep_csr=False):
     init_process_group()
     eng = solver.Engine(m, n, p, block=rank, nblocks=world, s=s, max_restart=max_restart, device=local, keep_csr=keep_csr)
     if world > 1:
-        connect_blocks(rank, world, eng.comm_export, eng.comm_connect, solver.comm_unique_id, eng.comm_init)
+        connect_blocks(rank, world, eng.comm_export, eng.comm_connect, solver.comm_unique_id, eng.comm_init,
+                       eng.comm_connect_block)
     return eng

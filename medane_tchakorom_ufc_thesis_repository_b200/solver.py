@@ -221,6 +221,9 @@ class Engine:
     def comm_connect(self, side: int, handle: bytes):
         check(_lib.lib().msp_comm_connect(self.h, side, handle))
 
+    def comm_connect_block(self, block: int, handle: bytes):
+        check(_lib.lib().msp_comm_connect_block(self.h, block, handle))
+
     def solve(self, alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_outer=0, record_history=True, profile=False):
         o = make_solve_opts(alg, s, rtol, inner, max_outer, record_history, profile=profile)
         res = Result()

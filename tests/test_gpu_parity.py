@@ -298,6 +298,35 @@ def test_config1_msm_512(S, oracle):
     grp.close()
 
 
+@pytest.mark.parametrize("alg,s", [("AM", 0), ("AMAM_GLOBAL", 4), ("AMAM_SEMI_LOCAL", 4), ("AMAM_LOCAL", 4)])
+def test_async_scheduled_matches_oracle(S, oracle, alg, s):
+    """Asynchronous drivers under the oracle's deterministic schedule (block 1 runs every second tick): same number
+    of steps per block until the device-side convergence detection reaches FINISHED everywhere, same final residual."""
+    inner = dict(restart=30, max_it=3, rtol=1e-10, abstol=1e-100)
+    ref = oracle.solve(alg, 24, 24, nblocks=2, s=s, rtol=1e-5, inner=inner, periods=[1, 2], max_outer=4000)
+    assert ref["rc"] == 0
+    grp = S.Group(24, 24, nblocks=2, s=s, max_restart=30)
+    res = grp.solve(alg, s=s, rtol=1e-5, inner=S.ksp_opts(**inner), max_outer=4000, periods=[1, 2])
+    its = [r["outer_its"] for r in res]
+    assert all(abs(a - b) <= 2 for a, b in zip(its, ref["outer_its_block"])), (its, ref["outer_its_block"])
+    assert res[0]["final_residual"] <= 1e-4 * res[0]["norm0"]
+    assert abs(res[0]["final_residual"] - ref["final_residual"]) <= 0.25 * ref["final_residual"]
+    x = grp.solution()
+    assert np.linalg.norm(x - ref["x"]) <= 1e-4 * np.linalg.norm(ref["x"])
+    grp.close()
+
+
+@pytest.mark.parametrize("alg,s,G", [("AM", 0, 2), ("AMAM_GLOBAL", 3, 4), ("AMAM_LOCAL", 3, 2)])
+def test_async_free_running_reaches_residual(S, alg, s, G):
+    """Barrier-free run (one host thread per block, no schedule): judged on the true residual after the closing
+    synchronous exchange, as north_star prescribes for the asynchronous variants."""
+    grp = S.Group(32, 32, nblocks=G, s=s, max_restart=30)
+    res = grp.solve(alg, s=s, rtol=1e-5, inner=S.ksp_opts(restart=30, max_it=3, rtol=1e-10, abstol=1e-100), max_outer=20000)
+    assert all(r["outer_its"] > 0 for r in res)
+    assert res[0]["final_residual"] <= 2e-4 * res[0]["norm0"]
+    grp.close()
+
+
 def test_errors(S):
     with pytest.raises(S.MsplitError):
         S.Engine(10, 10, nblocks=3)  # grid lines not divisible by the block count
