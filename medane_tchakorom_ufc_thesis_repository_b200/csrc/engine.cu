@@ -328,9 +328,17 @@ static void launch_mdot(msp_engine *e, int nv, const double *V, long long ldv, c
   a.per_group = (nv + ngroups - 1) / ngroups;
   ngroups = (nv + a.per_group - 1) / a.per_group;
   int per_sm = std::max(1, 8 / ngroups);
-  dim3 grid(grid_for((long long)e->nb / 4, per_sm), ngroups);
   e->prof_begin(1, 8.0 * e->nb * (nv + 1));
-  k_mdot<<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws);
+  if (a.per_group <= 2) {
+    dim3 grid(grid_for((long long)e->nb / 16, per_sm), ngroups);
+    k_mdot<2, 8><<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws);
+  } else if (a.per_group <= 4) {
+    dim3 grid(grid_for((long long)e->nb / 8, per_sm), ngroups);
+    k_mdot<4, 4><<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws);
+  } else {
+    dim3 grid(grid_for((long long)e->nb / 4, per_sm), ngroups);
+    k_mdot<8, 2><<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws);
+  }
   e->prof_end();
   e->launches++;
 }
@@ -342,7 +350,7 @@ static void launch_maxpy(msp_engine *e, int nv, const double *V, long long ldv, 
   a.nb = e->nb; a.nv = nv; a.ld = ldv; a.V = V; a.coef = coef; a.w = w; a.norm_out = norm_out; a.ctl = e->ctl;
   a.guard_it = guard_it; a.guard_refine = guard_refine; a.pass = pass; a.last_pass = 1;
   e->prof_begin(2, 8.0 * e->nb * (nv + 2));
-  k_maxpy_norm<FIN><<<grid_for((long long)e->nb / 2, 8), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot);
+  k_maxpy_norm<FIN><<<grid_for((long long)e->nb / 4, 8), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot);
   e->prof_end();
   e->launches++;
 }

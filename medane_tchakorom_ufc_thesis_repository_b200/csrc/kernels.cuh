@@ -373,6 +373,7 @@ struct MdotArgs {
   int guard_it, guard_refine; // guard_refine: run only if ctl->refine (second CGS pass)
 };
 
+template <int NVMAX, int U>
 __global__ void __launch_bounds__(MSPK_THREADS) k_mdot(MdotArgs a, ReduceWs ws) {
   if (a.guard_it >= 0) {
     if (!a.ctl->active || a.ctl->it != a.guard_it) return;
@@ -382,35 +383,37 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_mdot(MdotArgs a, ReduceWs ws) 
   const int v0 = g * a.per_group;
   const int nv = min(a.per_group, a.nv - v0);
   const double *Vg = a.V + (long long)v0 * a.ld;
-  double acc[8];
+  double acc[NVMAX];
 #pragma unroll
-  for (int v = 0; v < 8; v++) acc[v] = 0.0;
+  for (int v = 0; v < NVMAX; v++) acc[v] = 0.0;
   const long long npairs = a.nb >> 1;
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  for (; p + stride < npairs; p += 2 * stride) {
-    const double2 w0 = ld_stream2(a.w + 2 * p);
-    const double2 w1 = ld_stream2(a.w + 2 * (p + stride));
-    double2 x0[8], x1[8];
+  // U row-pairs per thread per trip: U * (NVMAX + 1) independent 16-byte loads in flight
+  for (; p + (U - 1) * stride < npairs; p += U * stride) {
+    double2 w[U], x[U][NVMAX];
 #pragma unroll
-    for (int v = 0; v < 8; v++)
+    for (int u = 0; u < U; u++) w[u] = ld_stream2(a.w + 2 * (p + u * stride));
+#pragma unroll
+    for (int v = 0; v < NVMAX; v++)
       if (v < nv) {
-        x0[v] = ld_stream2(Vg + v * a.ld + 2 * p);
-        x1[v] = ld_stream2(Vg + v * a.ld + 2 * (p + stride));
+#pragma unroll
+        for (int u = 0; u < U; u++) x[u][v] = ld_stream2(Vg + v * a.ld + 2 * (p + u * stride));
       }
 #pragma unroll
-    for (int v = 0; v < 8; v++)
+    for (int v = 0; v < NVMAX; v++)
       if (v < nv) {
-        acc[v] = fma(x0[v].x, w0.x, acc[v]);
-        acc[v] = fma(x0[v].y, w0.y, acc[v]);
-        acc[v] = fma(x1[v].x, w1.x, acc[v]);
-        acc[v] = fma(x1[v].y, w1.y, acc[v]);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          acc[v] = fma(x[u][v].x, w[u].x, acc[v]);
+          acc[v] = fma(x[u][v].y, w[u].y, acc[v]);
+        }
       }
   }
   for (; p < npairs; p += stride) {
     const double2 w0 = ld_stream2(a.w + 2 * p);
 #pragma unroll
-    for (int v = 0; v < 8; v++)
+    for (int v = 0; v < NVMAX; v++)
       if (v < nv) {
         const double2 x0 = ld_stream2(Vg + v * a.ld + 2 * p);
         acc[v] = fma(x0.x, w0.x, acc[v]);
@@ -420,14 +423,14 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_mdot(MdotArgs a, ReduceWs ws) 
   if ((a.nb & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const double wl = a.w[a.nb - 1];
 #pragma unroll
-    for (int v = 0; v < 8; v++)
+    for (int v = 0; v < NVMAX; v++)
       if (v < nv) acc[v] = fma(Vg[v * a.ld + a.nb - 1], wl, acc[v]);
   }
   __shared__ double sm[32];
   __shared__ bool last;
   const int slot = 8 + g; // reduce slots 8.. are MDot groups
 #pragma unroll
-  for (int v = 0; v < 8; v++) {
+  for (int v = 0; v < NVMAX; v++) {
     if (v < nv) {
       double bs = block_sum(acc[v], sm);
       if (threadIdx.x == 0) ws.partial[(slot * 8 + v) * (long long)MSPK_MAX_PART + blockIdx.x] = bs;
@@ -480,22 +483,53 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
   __syncthreads();
   double nrm = 0.0;
   const long long npairs = a.nb >> 1;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npairs; p += (long long)gridDim.x * blockDim.x) {
-    double2 t = *reinterpret_cast<const double2 *>(a.w + 2 * p);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  // two row-pairs per thread per trip, 8 basis vectors per chunk: 16 independent 16-byte loads in flight
+  for (; p + stride < npairs; p += 2 * stride) {
+    double2 t0 = __ldcs(reinterpret_cast<const double2 *>(a.w + 2 * p));
+    double2 t1 = __ldcs(reinterpret_cast<const double2 *>(a.w + 2 * (p + stride)));
     int j = 0;
     for (; j + 8 <= a.nv; j += 8) {
-      double2 x[8];
+      double2 x0[8], x1[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) x[u] = ld_stream2(a.V + (long long)(j + u) * a.ld + 2 * p);
+      for (int u = 0; u < 8; u++) {
+        x0[u] = ld_stream2(a.V + (long long)(j + u) * a.ld + 2 * p);
+        x1[u] = ld_stream2(a.V + (long long)(j + u) * a.ld + 2 * (p + stride));
+      }
 #pragma unroll
-      for (int u = 0; u < 8; u++) { t.x = fma(cf[j + u], x[u].x, t.x); t.y = fma(cf[j + u], x[u].y, t.y); }
+      for (int u = 0; u < 8; u++) {
+        const double c = cf[j + u];
+        t0.x = fma(c, x0[u].x, t0.x); t0.y = fma(c, x0[u].y, t0.y);
+        t1.x = fma(c, x1[u].x, t1.x); t1.y = fma(c, x1[u].y, t1.y);
+      }
     }
     if (j < a.nv) {
-      double2 x[8];
+      double2 x0[8], x1[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) if (j + u < a.nv) x[u] = ld_stream2(a.V + (long long)(j + u) * a.ld + 2 * p);
+      for (int u = 0; u < 8; u++)
+        if (j + u < a.nv) {
+          x0[u] = ld_stream2(a.V + (long long)(j + u) * a.ld + 2 * p);
+          x1[u] = ld_stream2(a.V + (long long)(j + u) * a.ld + 2 * (p + stride));
+        }
 #pragma unroll
-      for (int u = 0; u < 8; u++) if (j + u < a.nv) { t.x = fma(cf[j + u], x[u].x, t.x); t.y = fma(cf[j + u], x[u].y, t.y); }
+      for (int u = 0; u < 8; u++)
+        if (j + u < a.nv) {
+          const double c = cf[j + u];
+          t0.x = fma(c, x0[u].x, t0.x); t0.y = fma(c, x0[u].y, t0.y);
+          t1.x = fma(c, x1[u].x, t1.x); t1.y = fma(c, x1[u].y, t1.y);
+        }
+    }
+    __stcs(reinterpret_cast<double2 *>(a.w + 2 * p), t0);
+    __stcs(reinterpret_cast<double2 *>(a.w + 2 * (p + stride)), t1);
+    nrm = fma(t0.x, t0.x, fma(t0.y, t0.y, nrm));
+    nrm = fma(t1.x, t1.x, fma(t1.y, t1.y, nrm));
+  }
+  for (; p < npairs; p += stride) {
+    double2 t = *reinterpret_cast<const double2 *>(a.w + 2 * p);
+    for (int j = 0; j < a.nv; j++) {
+      const double2 x = ld_stream2(a.V + (long long)j * a.ld + 2 * p);
+      t.x = fma(cf[j], x.x, t.x); t.y = fma(cf[j], x.y, t.y);
     }
     *reinterpret_cast<double2 *>(a.w + 2 * p) = t;
     nrm = fma(t.x, t.x, fma(t.y, t.y, nrm));
