@@ -1,0 +1,244 @@
+/*
+ * msolve.c — C host driver of the multisplitting solve path (one binary for every --alg).
+ *
+ * Replaces the reference's nine main() programs (src/<alg>/<alg>.c, makefile:120-148) and the command line
+ * iSolve builds (iSolve:347-401).  It accepts the reference's PETSc-style options — application options
+ * -m -n -s -npb -rtol (…-global.c:74-78), -atol (gmres_solution.c:45), -min_convergence_count (parsed, unused by
+ * the _prime drivers), per-block KSP prefixes inner{K}_ / outer{K}_ (…multisplitting.c:129-143) and the iSolve
+ * spelling inner_ / outer_ for "all blocks", un-prefixed -ksp_* for the stand-alone GMRES — ignores unknown keys
+ * like the PETSc options database does, and prints the log lines the reference's log scrapers rely on
+ * (utils.c:668-729).  All numerics happen behind the C-ABI of libmsplit.so (include/msplit.h).
+ *
+ * Extensions: -alg <iSolve name | reference binary name>, -p <depth> (3-D, poisson3DMatrix), -nblocks G
+ * (default: the reference's np/npb = 2; 1 for GMRES), -devices 0,1,... (one entry per block, default: block K on
+ * GPU K mod #GPUs), -max_outer N, -period a,b,... (deterministic asynchronous schedule, tests only).
+ */
+#include "../../include/msplit.h"
+
+#include <ctype.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { int argc; char **argv; } optdb;
+
+static const char *opt_find(const optdb *db, const char *key, int *present) {
+  /* last occurrence wins, like the PETSc options database */
+  const char *val = NULL;
+  if (present) *present = 0;
+  for (int i = 1; i < db->argc; i++) {
+    if (strcmp(db->argv[i], key) == 0) {
+      if (present) *present = 1;
+      val = (i + 1 < db->argc && !(db->argv[i + 1][0] == '-' && isalpha((unsigned char)db->argv[i + 1][1]))) ? db->argv[i + 1] : "";
+    }
+  }
+  return val;
+}
+static int opt_int(const optdb *db, const char *key, int *out) {
+  const char *v = opt_find(db, key, NULL);
+  if (!v || !*v) return 0;
+  *out = atoi(v);
+  return 1;
+}
+static int opt_real(const optdb *db, const char *key, double *out) {
+  const char *v = opt_find(db, key, NULL);
+  if (!v || !*v) return 0;
+  *out = atof(v);
+  return 1;
+}
+static int opt_flag(const optdb *db, const char *key) {
+  int present = 0;
+  const char *v = opt_find(db, key, &present);
+  if (!present) return 0;
+  if (v && *v && (strcmp(v, "0") == 0 || strcasecmp(v, "false") == 0 || strcasecmp(v, "no") == 0)) return 0;
+  return 1;
+}
+
+static void ksp_defaults(msp_ksp_opts *o) {
+  /* PETSc 3.22.1 defaults, tmp/petscmpiexec_help:336-342,602-615 */
+  o->restart = 30; o->max_it = 10000; o->rtol = 1e-5; o->abstol = 1e-50; o->divtol = 1e4;
+  o->initial_rtol = 0; o->guess_nonzero = 0; o->cgs_refine = 0; o->mgs = 0; o->min_it = 0;
+}
+
+/* read -<prefix>ksp_* into o; returns -1 on an unsupported value */
+static int ksp_from_options(const optdb *db, const char *prefix, msp_ksp_opts *o) {
+  char key[128];
+  const char *v;
+#define KEY(name) (snprintf(key, sizeof key, "-%s%s", prefix, name), key)
+  opt_int(db, KEY("ksp_gmres_restart"), &o->restart);
+  opt_int(db, KEY("ksp_max_it"), &o->max_it);
+  opt_real(db, KEY("ksp_rtol"), &o->rtol);
+  opt_real(db, KEY("ksp_atol"), &o->abstol);
+  opt_real(db, KEY("ksp_divtol"), &o->divtol);
+  opt_int(db, KEY("ksp_min_it"), &o->min_it);
+  if (opt_flag(db, KEY("ksp_converged_use_initial_residual_norm"))) o->initial_rtol = 1;
+  if (opt_flag(db, KEY("ksp_gmres_modifiedgramschmidt"))) o->mgs = 1;
+  v = opt_find(db, KEY("ksp_gmres_cgs_refinement_type"), NULL);
+  if (v && *v) {
+    if (!strcasecmp(v, "refine_never")) o->cgs_refine = 0;
+    else if (!strcasecmp(v, "refine_ifneeded")) o->cgs_refine = 1;
+    else if (!strcasecmp(v, "refine_always")) o->cgs_refine = 2;
+    else { fprintf(stderr, "msolve: unknown %s %s\n", key, v); return -1; }
+  }
+  v = opt_find(db, KEY("ksp_type"), NULL);
+  if (v && *v && strcasecmp(v, "gmres")) { fprintf(stderr, "msolve: -%sksp_type %s is not on the device path (gmres only)\n", prefix, v); return -1; }
+  v = opt_find(db, KEY("pc_type"), NULL);
+  if (v && *v && strcasecmp(v, "none")) { fprintf(stderr, "msolve: -%spc_type %s is not supported (none only)\n", prefix, v); return -1; }
+  v = opt_find(db, KEY("ksp_norm_type"), NULL);
+  if (v && *v && strcasecmp(v, "unpreconditioned") && strcasecmp(v, "preconditioned") && strcasecmp(v, "default")) {
+    fprintf(stderr, "msolve: -%sksp_norm_type %s is not supported\n", prefix, v); return -1; /* pc none: both norms coincide */
+  }
+#undef KEY
+  return 0;
+}
+
+static int alg_from_name(const char *s) {
+  static const struct { const char *name; int alg; } tab[] = {
+    {"SM", MSP_ALG_SM}, {"MSM", MSP_ALG_SM}, {"synchronous-multisplitting", MSP_ALG_SM},
+    {"SMSM_GLOBAL", MSP_ALG_SMSM_GLOBAL}, {"synchronous-multisplitting-synchronous-minimization-global", MSP_ALG_SMSM_GLOBAL},
+    {"SMSM_SEMI_LOCAL", MSP_ALG_SMSM_SEMI_LOCAL}, {"synchronous-multisplitting-synchronous-minimization-semi-local", MSP_ALG_SMSM_SEMI_LOCAL},
+    {"SMSM_LOCAL", MSP_ALG_SMSM_LOCAL}, {"synchronous-multisplitting-synchronous-minimization-local", MSP_ALG_SMSM_LOCAL},
+    {"GMRES", MSP_ALG_GMRES}, {"gmres_solution", MSP_ALG_GMRES},
+    {"AM", MSP_ALG_AM}, {"asynchronous-multisplitting_prime", MSP_ALG_AM}, {"asynchronous-multisplitting", MSP_ALG_AM},
+    {"AMAM_GLOBAL", MSP_ALG_AMAM_GLOBAL}, {"asynchronous-multisplitting-asynchronous-minimization-global_prime", MSP_ALG_AMAM_GLOBAL},
+    /* iSolve:56 maps AMAM_SEMI_LOCAL to the *local* binary; dispatched correctly here */
+    {"AMAM_SEMI_LOCAL", MSP_ALG_AMAM_SEMI_LOCAL}, {"asynchronous-multisplitting-asynchronous-minimization-semi-local_prime", MSP_ALG_AMAM_SEMI_LOCAL},
+    {"AMAM_LOCAL", MSP_ALG_AMAM_LOCAL}, {"asynchronous-multisplitting-asynchronous-minimization-local_prime", MSP_ALG_AMAM_LOCAL},
+  };
+  for (size_t i = 0; i < sizeof tab / sizeof tab[0]; i++) if (!strcasecmp(s, tab[i].name)) return tab[i].alg;
+  return -1;
+}
+
+static int parse_int_list(const char *s, int *out, int cap) {
+  int n = 0;
+  while (s && *s && n < cap) {
+    out[n++] = atoi(s);
+    s = strchr(s, ',');
+    if (s) s++;
+  }
+  return n;
+}
+
+#define CHECK(call)                                                      \
+  do {                                                                   \
+    if ((call) != 0) {                                                   \
+      fprintf(stderr, "msolve: %s\n  at %s\n", msp_last_error(), #call); \
+      return 1;                                                          \
+    }                                                                    \
+  } while (0)
+
+int main(int argc, char **argv) {
+  optdb db = {argc, argv};
+  /* defaults of config/default_run_variables */
+  int m = 1024, n = 1024, p = 1, s = 4, npb = 1, nblocks = -1, max_outer = 0, min_cc = 4;
+  double rtol = 1e-3, atol = 1e-100;
+  const char *algname = opt_find(&db, "-alg", NULL);
+  if (!algname || !*algname) algname = opt_find(&db, "--alg", NULL);
+  if (!algname || !*algname) {
+    const char *base = strrchr(argv[0], '/');
+    algname = base ? base + 1 : argv[0]; /* reference binaries are one per algorithm */
+    if (alg_from_name(algname) < 0) algname = "AM"; /* DEFAULT_ALGORITHM */
+  }
+  const int alg = alg_from_name(algname);
+  if (alg < 0) { fprintf(stderr, "msolve: unknown algorithm %s\n", algname); return 2; }
+  opt_int(&db, "-m", &m); opt_int(&db, "-n", &n); opt_int(&db, "-p", &p); opt_int(&db, "-s", &s);
+  opt_int(&db, "-npb", &npb); opt_real(&db, "-rtol", &rtol); opt_real(&db, "-atol", &atol);
+  opt_int(&db, "-min_convergence_count", &min_cc); opt_int(&db, "-max_outer", &max_outer);
+  opt_int(&db, "-nblocks", &nblocks);
+  if (npb != 1) fprintf(stderr, "msolve: -npb %d ignored: a Jacobi block is one GPU here\n", npb);
+  if (nblocks < 0) nblocks = (alg == MSP_ALG_GMRES) ? 1 : 2; /* iSolve:332-338: np/npb == 2 */
+  if (nblocks > MSP_MAX_BLOCKS) { fprintf(stderr, "msolve: too many blocks\n"); return 2; }
+  const int uses_s = !(alg == MSP_ALG_SM || alg == MSP_ALG_AM || alg == MSP_ALG_GMRES);
+
+  msp_ksp_opts inner;
+  ksp_defaults(&inner);
+  if (alg == MSP_ALG_GMRES) {
+    if (ksp_from_options(&db, "", &inner)) return 2;
+  } else {
+    /* "inner_" (iSolve:349) = all blocks; inner{K}_ per block.  One option set drives every block: the reference's
+     * command lines always give identical values; differing sets are rejected instead of silently merged. */
+    if (ksp_from_options(&db, "inner_", &inner)) return 2;
+    msp_ksp_opts first = inner;
+    for (int k = 1; k <= nblocks; k++) {
+      char pre[32];
+      snprintf(pre, sizeof pre, "inner%d_", k);
+      msp_ksp_opts o = inner;
+      if (ksp_from_options(&db, pre, &o)) return 2;
+      if (k == 1) first = o;
+      else if (memcmp(&o, &first, sizeof o)) { fprintf(stderr, "msolve: -inner%d_* differs from -inner1_*: per-block inner options must agree\n", k); return 2; }
+    }
+    inner = first;
+    /* outer{K}_ksp_* select the reference's LSQR/CG settings; the device minimiser is an exact least-squares solve
+     * (TSQR), so they are accepted and ignored — exactly what "-options_left" would report as unused */
+  }
+
+  int devices[MSP_MAX_BLOCKS], periods[MSP_MAX_BLOCKS];
+  const int ngpu = msp_device_count();
+  if (ngpu < 1) { fprintf(stderr, "msolve: no CUDA device (there is no CPU fallback)\n"); return 3; }
+  for (int k = 0; k < nblocks; k++) devices[k] = k % ngpu;
+  const char *dl = opt_find(&db, "-devices", NULL);
+  if (dl && *dl) { int got = parse_int_list(dl, devices, nblocks); for (int k = got; k < nblocks; k++) devices[k] = devices[k % (got ? got : 1)]; }
+  memset(periods, 0, sizeof periods);
+  const char *pl = opt_find(&db, "-period", NULL);
+  if (pl && *pl) parse_int_list(pl, periods, nblocks);
+
+  msp_problem prob;
+  memset(&prob, 0, sizeof prob);
+  prob.dim = p > 1 ? 3 : 2; prob.m = m; prob.n = n; prob.p = p; prob.nblocks = nblocks;
+  prob.s = uses_s ? s : 0; prob.max_restart = inner.restart; prob.keep_csr = 0;
+
+  if (alg == MSP_ALG_GMRES) {
+    /* gmres_solution.c:50-85 */
+    msp_engine *e = NULL;
+    msp_result res;
+    if (m != n) { fprintf(stderr, "msolve: poisson2DMatrix_complete assumes a square mesh (utils.c:390)\n"); return 2; }
+    CHECK(msp_create(&prob, devices[0], &e));
+    msp_ksp_opts o = inner;
+    if (opt_find(&db, "-ksp_rtol", NULL) == NULL) o.rtol = 1e-5;
+    printf("Start solving...\n");
+    CHECK(msp_gmres_solve(e, &o, &res));
+    printf("End solving...\n\n\n");
+    printf("Elapsed time (iterations):   %f  seconds \n", res.elapsed_s);
+    printf("======================== \n");
+    printf("Number of iterations of GMRES : %d \n", res.gmres_its);
+    printf("Right hand side norm : %e \n", res.norm0);
+    printf("GMRES residual norm : %e \n", res.gmres_rnorm);
+    printf("||r(i)||/||b|| : %e \n", res.gmres_rnorm / res.norm0);
+    printf("======================== \n");
+    printf("Erreur : %e \n", res.error);
+    printf("\n\n");
+    msp_destroy(e);
+    return 0;
+  }
+
+  msp_group *g = NULL;
+  CHECK(msp_group_create(&prob, nblocks, devices, &g));
+  msp_solve_opts so;
+  memset(&so, 0, sizeof so);
+  so.alg = alg; so.s = uses_s ? s : 0; so.rtol = rtol; so.inner = inner; so.max_outer = max_outer; so.record_history = 1;
+  for (int k = 0; k < nblocks; k++) so.period[k] = periods[k];
+  msp_result *res = (msp_result *)calloc((size_t)nblocks, sizeof(msp_result));
+  CHECK(msp_group_solve(g, &so, res));
+
+  printf("Global norm of b %e \n", res[0].norm0); /* …multisplitting.c:157 */
+  if (opt_flag(&db, "-print_history"))
+    for (int i = 0; i < res[0].hist_len; i++) printf("Final residual norm 2 = %e \n", res[0].hist[i]); /* …multisplitting.c:195 */
+  double elapsed = 0.0;
+  for (int k = 0; k < nblocks; k++) if (res[k].elapsed_s > elapsed) elapsed = res[k].elapsed_s;
+  printf("Elapsed time (iterations):   %f  seconds \n", elapsed); /* utils.c:671 */
+  for (int k = 0; k < nblocks; k++) {
+    if (uses_s) printf("[ Block rank %d ] Total number of iterations (outer_iterations * s) = %d * %d = %d \n", k, res[k].outer_its, s, s * res[k].outer_its); /* utils.c:727 */
+    else printf("[ Block rank %d ] Total number of iterations (outer_iterations) = %d \n", k, res[k].outer_its); /* utils.c:706 */
+  }
+  printf("Final residual norm 2 = %e \n", res[0].final_residual); /* utils.c:699 */
+  printf("Erreur : %e \n", res[0].error);                        /* …multisplitting.c:229 */
+  long long launches = 0;
+  for (int k = 0; k < nblocks; k++) launches += (long long)res[k].kernel_launches;
+  printf("[msolve] alg=%s blocks=%d gpus=%d rel_residual=%e kernel_launches=%lld\n", algname, nblocks, ngpu,
+         res[0].final_residual / res[0].norm0, launches);
+  free(res);
+  msp_group_destroy(g);
+  (void)atol;
+  return 0;
+}

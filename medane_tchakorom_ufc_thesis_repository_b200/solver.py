@@ -128,6 +128,13 @@ class Engine:
     def x(self, v):
         check(_lib.lib().msp_set_x(self.h, np.ascontiguousarray(v, np.float64)))
 
+    def get_x(self, out=None):
+        """msp_get_x straight into a caller-owned (e.g. pinned) host array."""
+        if out is None:
+            return self.x
+        check(_lib.lib().msp_get_x(self.h, out))
+        return out
+
     @property
     def rhs(self):
         return self._getv(_lib.lib().msp_get_rhs, self.nb)

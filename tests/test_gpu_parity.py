@@ -352,3 +352,40 @@ def test_one_process_per_gpu_path(S):
                           "127.0.0.1", "--master-port", "29571", os.path.join(root, "tools", "mgpu_check.py")],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MGPU OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_msolve_c_driver(S, oracle):
+    """The C host driver: reference option names in, reference log lines out, same iteration count as the oracle."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "bin", "msolve")
+    assert os.path.exists(exe), "bin/msolve missing: run __graft_entry__.build()"
+    cmd = [exe, "-alg", "SMSM_GLOBAL", "-npb", "1", "-m", "32", "-n", "32", "-rtol", "1e-6", "-s", "5"]
+    for k in (1, 2):
+        cmd += [f"-inner{k}_ksp_type", "gmres", f"-inner{k}_ksp_gmres_preallocate", f"-inner{k}_ksp_gmres_restart", "30",
+                f"-inner{k}_ksp_atol", "1e-100", f"-inner{k}_ksp_max_it", "5", f"-inner{k}_ksp_rtol", "1e-10",
+                f"-inner{k}_pc_type", "none", f"-inner{k}_ksp_norm_type", "UNPRECONDITIONED",
+                f"-outer{k}_ksp_type", "lsqr", f"-outer{k}_ksp_max_it", "70", f"-outer{k}_ksp_rtol", "1e-15", f"-outer{k}_pc_type", "none"]
+    cmd += ["-options_left", "-log_view"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    ref = oracle.solve("SMSM_GLOBAL", 32, 32, nblocks=2, s=5, rtol=1e-6, inner=dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100))
+    m = re.search(r"\[ Block rank 0 \] Total number of iterations \(outer_iterations \* s\) = (\d+) \* 5 = (\d+)", out.stdout)
+    assert m and abs(int(m.group(1)) - ref["outer_its"]) <= 1 and int(m.group(2)) == 5 * int(m.group(1)), out.stdout
+    assert re.search(r"Elapsed time \(iterations\):\s+[0-9.]+\s+seconds", out.stdout)
+    fr = float(re.search(r"Final residual norm 2 = ([0-9.e+-]+)", out.stdout).group(1))
+    assert fr <= 1e-6 * ref["norm0"] * 1.000001
+    assert re.search(r"Erreur : [0-9.e+-]+", out.stdout)
+    # stand-alone GMRES binary name + un-prefixed options (running_bulk_test_local:40-45)
+    out = subprocess.run([exe, "-alg", "gmres_solution", "-m", "32", "-n", "32", "-ksp_type", "gmres", "-ksp_rtol", "1e-4", "-ksp_atol", "1e-100",
+                          "-ksp_max_it", "1000000000", "-pc_type", "none", "-ksp_norm_type", "UNPRECONDITIONED",
+                          "-ksp_converged_use_initial_residual_norm", "-ksp_gmres_restart", "30"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rp, ci, va = oracle.poisson2d_complete(32, 32)
+    b = oracle.spmv(rp, ci, va, np.ones(1024))
+    _, its, _, _ = oracle.gmres(rp, ci, va, b, restart=30, rtol=1e-4, abstol=1e-100, max_it=10 ** 9, initial_rtol=1)
+    assert int(re.search(r"Number of iterations of GMRES : (\d+)", out.stdout).group(1)) == its
+    # unsupported inner solver is refused loudly, not silently replaced
+    out = subprocess.run([exe, "-alg", "SM", "-m", "16", "-n", "16", "-inner1_ksp_type", "preonly"], capture_output=True, text=True, timeout=60)
+    assert out.returncode != 0 and "not on the device path" in out.stderr
