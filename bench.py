@@ -134,11 +134,20 @@ def run_reference(args):
 
 
 def workload_config(args, G):
+    if args.p > 1:
+        rows = args.m * args.n * args.p
+        nnz = 7 * rows - 2 * (args.m * args.n + args.n * args.p + args.m * args.p)
+        grid = f"3-D 7-pt Poisson {args.m}x{args.n}x{args.p}"
+    else:
+        rows = args.m * args.n
+        nnz = 5 * rows - 2 * args.m - 2 * args.n
+        grid = f"2-D 5-pt Poisson {args.m}x{args.n}"
+    which = {"SMSM_GLOBAL": "BASELINE configs[2]", "SMSM_SEMI_LOCAL": "BASELINE configs[3]", "AMAM_GLOBAL": "BASELINE configs[4]"}.get(args.alg, "")
     return {
-        "workload": f"SMSM global minimisation s={S_BASIS}, 2-D 5-pt Poisson {args.m}x{args.n} (BASELINE configs[2]), "
+        "workload": f"{args.alg} s={S_BASIS}, {grid} ({which}), "
                     f"inner GMRES(30) max_it 20 rtol 1e-10 UIR, exact LS (TSQR), rtol 1e-6",
         "step": "one outer iteration = 5 x (rhs update, inner GMRES <=20 Arnoldi steps, boundary exchange) + A*S + TSQR + x=S*alpha",
-        "rows": args.m * args.n, "nnz": 5 * args.m * args.n - 2 * args.m - 2 * args.n, "blocks": G,
+        "rows": rows, "nnz": nnz, "blocks": G,
         "parallelism": f"strip{G} (one Jacobi block per GPU)",
         "l2_policy": "inputs larger than L2 (each vector >= 67 MB per GPU, matrix >= 500 MB per GPU); no flush",
     }
@@ -157,12 +166,12 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     peaks, peak_src = measured_peaks()
-    eng = D.make_distributed_engine(args.m, args.n, 1, s=S_BASIS, max_restart=INNER["restart"])
+    eng = D.make_distributed_engine(args.m, args.n, args.p, s=S_BASIS, max_restart=INNER["restart"])
     inner = S.ksp_opts(**INNER)
     n_local = eng.nb
 
     def steps(k, profile=False):
-        return eng.solve("SMSM_GLOBAL", s=S_BASIS, rtol=RTOL, inner=inner, max_outer=k, record_history=True, profile=profile)
+        return eng.solve(args.alg, s=S_BASIS, rtol=RTOL, inner=inner, max_outer=k, record_history=True, profile=profile)
 
     # ---- warm-up (W outer iterations, untimed) ----
     if args.warmup > 0:
@@ -177,7 +186,7 @@ def run_gpu(args):
     D.barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
-    assert res["outer_its"] == args.steps or res["last_norm"] <= RTOL * res["norm0"]
+    assert res["outer_its"] == args.steps or res["last_norm"] <= RTOL * res["norm0"] or args.alg.startswith("A")
     k_done = res["outer_its"]
     t_dev = D.reduce_max(res["elapsed_s"])
     launches = int(D.reduce_sum(float(res["kernel_launches"])))
@@ -225,7 +234,8 @@ def run_gpu(args):
 
     rel = res["last_norm"] / res["norm0"]
     line = {
-        "metric": "smsm_global_seconds_per_outer_iteration", "value": per_step, "unit": "s/outer-iteration",
+        "metric": "smsm_global_seconds_per_outer_iteration" if args.alg == "SMSM_GLOBAL" else f"{args.alg.lower()}_seconds_per_outer_iteration",
+        "value": per_step, "unit": "s/outer-iteration",
         "n_gpus": world, "steps": k_done, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (b = A*1, x0 = 0; deterministic, no RNG)",
@@ -240,7 +250,7 @@ def run_gpu(args):
                 "d2h_bytes_per_step": int(8 * n_local * world), "steps": e2e_steps},
         "gpu_launches": launches,
     }
-    if rank == 0 and not args.no_cpu_baseline and world == 1:
+    if rank == 0 and not args.no_cpu_baseline and world == 1 and args.alg == "SMSM_GLOBAL" and args.p == 1:
         line["cpu_baseline"] = cpu_baseline(args)
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -282,6 +292,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--m", type=int, default=8192)
     ap.add_argument("--n", type=int, default=8192)
+    ap.add_argument("--p", type=int, default=1, help="depth: > 1 selects the 3-D 7-point problem (configs[3], configs[4])")
+    ap.add_argument("--alg", default="SMSM_GLOBAL", help="SMSM_GLOBAL (headline) | SMSM_SEMI_LOCAL | SMSM_LOCAL | SM | AMAM_GLOBAL | ...")
     ap.add_argument("--cpu-sample-n", type=int, default=2048, help="grid edge of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--to-rtol", type=int, default=0, help="run SMSM-global to rtol 1e-6 on an N x N grid and report seconds")

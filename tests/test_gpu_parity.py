@@ -328,6 +328,17 @@ def test_async_free_running_reaches_residual(S, alg, s, G):
     grp.close()
 
 
+def test_one_line_blocks(S, oracle):
+    """Edge case: every block is a single grid line, so each row couples to both neighbours."""
+    inner = dict(restart=30, max_it=4, rtol=1e-10, abstol=1e-100)
+    grp = S.Group(4, 16, nblocks=4, s=3, max_restart=30)
+    res = grp.solve("SMSM_GLOBAL", s=3, rtol=1e-8, inner=S.ksp_opts(**inner), max_outer=500)
+    ref = oracle.solve("SMSM_GLOBAL", 4, 16, nblocks=4, s=3, rtol=1e-8, inner=inner, max_outer=500)
+    assert abs(res[0]["outer_its"] - ref["outer_its"]) <= 1
+    assert res[0]["final_residual"] <= 1e-8 * res[0]["norm0"] * 1.000001
+    grp.close()
+
+
 def test_errors(S):
     with pytest.raises(S.MsplitError):
         S.Engine(10, 10, nblocks=3)  # grid lines not divisible by the block count
