@@ -290,9 +290,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--m", type=int, default=8192)
-    ap.add_argument("--n", type=int, default=8192)
-    ap.add_argument("--p", type=int, default=1, help="depth: > 1 selects the 3-D 7-point problem (configs[3], configs[4])")
+    # (long spellings exist because torchrun's own parser treats --m / --n / --p as ambiguous prefixes of its options)
+    ap.add_argument("--m", "--grid-lines", dest="m", type=int, default=8192)
+    ap.add_argument("--n", "--grid-columns", dest="n", type=int, default=8192)
+    ap.add_argument("--p", "--grid-depth", dest="p", type=int, default=1,
+                    help="depth: > 1 selects the 3-D 7-point problem (configs[3], configs[4])")
     ap.add_argument("--alg", default="SMSM_GLOBAL", help="SMSM_GLOBAL (headline) | SMSM_SEMI_LOCAL | SMSM_LOCAL | SM | AMAM_GLOBAL | ...")
     ap.add_argument("--cpu-sample-n", type=int, default=2048, help="grid edge of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

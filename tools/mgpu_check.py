@@ -30,7 +30,9 @@ for alg, m, n, p, s, rtol, inner in cases:
         ref = O.solve(alg, m, n, p=p, nblocks=world, s=s, rtol=rtol, inner=inner, max_outer=5000)
         x = np.concatenate([np.frombuffer(b, dtype=np.float64) for b in parts])
         dx = np.linalg.norm(x - ref["x"]) / np.linalg.norm(ref["x"])
-        good = abs(res["outer_its"] - ref["outer_its"]) <= 1 and (res["outer_its"] != ref["outer_its"] or dx <= 1e-8)
+        # +-1 outer iteration; solutions within the run's stopping tolerance (1e-8 only for short, well-conditioned
+        # runs: DESIGN.md §5)
+        good = abs(res["outer_its"] - ref["outer_its"]) <= 1 and (res["outer_its"] != ref["outer_its"] or dx <= max(1e-8, 100 * rtol))
         ok &= good
         print(f"{alg} {m}x{n}x{p} G={world}: its {res['outer_its']} (oracle {ref['outer_its']}), dx {dx:.2e}, "
               f"resid {res['final_residual'] / res['norm0']:.3e}, elapsed {res['elapsed_s'] * 1e3:.1f} ms {'ok' if good else 'FAIL'}", flush=True)
