@@ -11,6 +11,8 @@
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
+#include <map>
+#include <tuple>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -237,6 +239,11 @@ struct msp_engine {
     res->b_spmv = by[0]; res->b_mdot = by[1]; res->b_maxpy = by[2]; res->b_other = by[3];
     res->n_spmv = n[0]; res->n_mdot = n[1]; res->n_maxpy = n[2]; res->n_other = n[3];
   }
+  // CUDA graphs of whole restart cycles (launch-bound regime: small blocks), keyed by everything baked into the nodes
+  typedef std::tuple<int, int, int, const void *, const void *, const void *> CycleKey;
+  struct CycleGraph { cudaGraphExec_t exec; int launches; };
+  std::map<CycleKey, CycleGraph> cycle_graphs;
+  bool use_graphs = true;
   double local_sig = 0; // sticky convergence signal
   // deterministic turn taking for the emulated asynchronous schedule
   struct msp_group *grp = nullptr;
@@ -362,6 +369,7 @@ static int engine_free(msp_engine *e) {
   if (!e) return 0;
   cudaSetDevice(e->device);
   if (e->st) cudaStreamSynchronize(e->st);
+  for (auto &kv : e->cycle_graphs) cudaGraphExecDestroy(kv.second.exec);
   for (int J = 0; J < MSP_MAX_BLOCKS; J++)
     if (e->peer_any[J].base && e->peer_any_ipc[J]) cudaIpcCloseMemHandle(e->peer_any[J].base);
   void *ptrs[] = {e->rp, e->ci, e->va, e->ecol, e->eval, e->brow, e->b, e->rhs, e->x, e->halo[0], e->halo[1], e->V, e->Wb[0],
@@ -467,6 +475,7 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   if (ok && cudaMallocHost(&e->hsc, sizeof(double) * 256) != cudaSuccess) ok = false;
   if (!ok) { g_err = "out of device memory (vectors)"; return fail(1); }
   e->comm = new SelfComm(); e->own_comm = true;
+  e->use_graphs = getenv("MSPLIT_NO_GRAPHS") == nullptr;
   // ---- b_K = A_K,: * 1 (computeTheRightHandSideWithInitialGuess utils.c:626): halos of ones ----
   {
     k_fill<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, 1.0, e->Wb[0]);
@@ -539,49 +548,72 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
   double *peer_lo = (publish && e->peer[0].base) ? e->peer[0].halo(1, e->par) : nullptr; // lower neighbour's "hi" window
   double *peer_hi = (publish && e->peer[1].base) ? e->peer[1].halo(0, e->par) : nullptr; // upper neighbour's "lo" window
   while (true) {
-    // ---- cycle prologue: r = rhs - A x (or r = rhs), ||r|| and the cycle-begin logic on the device ----
-    if (first && guess_zero) {
-      k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, e->rhs, e->Wb[0]);
-      k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->rhs, 0.0, e->ws, 2, e->dsc + 9);
-      k_ctl_cycle_begin_from<<<1, 32, 0, e->st>>>(e->ctl, e->dsc + 9);
-      e->launches += 3;
+    const int nsteps = std::min(o->restart, o->max_it - itcount);
+    const bool from_rhs = first && guess_zero;
+    // everything one restart cycle enqueues: prologue, nsteps Arnoldi steps, solution update, 16-byte status read-back
+    auto enqueue_cycle = [&]() -> int {
+      // ---- cycle prologue: r = rhs - A x (or r = rhs), ||r|| and the cycle-begin logic on the device ----
+      if (from_rhs) {
+        k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, e->rhs, e->Wb[0]);
+        k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->rhs, 0.0, e->ws, 2, e->dsc + 9);
+        k_ctl_cycle_begin_from<<<1, 32, 0, e->st>>>(e->ctl, e->dsc + 9);
+        e->launches += 3;
+      } else {
+        SpmvArgs a = spmv_args(e, e->x, e->Wb[0]);
+        a.b = e->rhs;
+        launch_spmv_w<0, true, false, true>(e, a, 0, e->ctl);
+      }
+      int cur = 0; // Wb[cur] holds the un-normalised new basis vector
+      double *lhh = reinterpret_cast<double *>(reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, lhh));
+      for (int it = 0; it < nsteps; it++) {
+        // v_it = w/||w|| (deferred VecNormalize, K5) fused with w' = A v_it (K1)
+        SpmvArgs a = spmv_args(e, e->Wb[cur], e->Wb[cur ^ 1]);
+        a.vout = e->V + (long long)it * e->ld; a.guard_it = it;
+        launch_spmv_w<0, false, true, false>(e, a, 0, nullptr);
+        cur ^= 1;
+        // classical Gram-Schmidt: lhh = -V^T w (K3); w += V lhh, ||w|| (K4+K5), Hessenberg + test (K6)
+        launch_mdot(e, it + 1, e->V, e->ld, e->Wb[cur], lhh, -1.0, it, 0);
+        launch_maxpy<1>(e, it + 1, e->V, e->ld, lhh, e->Wb[cur], nullptr, it, 0, 0, 0);
+        if (o->cgs_refine) {
+          launch_mdot(e, it + 1, e->V, e->ld, e->Wb[cur], lhh, -1.0, it, 1);
+          launch_maxpy<1>(e, it + 1, e->V, e->ld, lhh, e->Wb[cur], nullptr, it, 1, 1, 0);
+        }
+      }
+      // ---- KSPGMRESBuildSoln + boundary publication ----
+      k_build_soln_coef<<<1, 32, 0, e->st>>>(e->ctl);
+      UpdateXArgs u{};
+      u.nb = e->nb; u.H = e->H; u.ld = e->ld; u.V = e->V; u.x = e->x; u.ctl = e->ctl; u.peer_lo = peer_lo; u.peer_hi = peer_hi;
+      k_update_x<<<grid_for(e->nb, 8), MSPK_THREADS, 0, e->st>>>(u);
+      e->launches += 2;
+      CK(cudaMemcpyAsync(e->hsc + 32, reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, its), 16, cudaMemcpyDeviceToHost, e->st));
+      return 0;
+    };
+    if (e->use_graphs && !e->prof) {
+      const msp_engine::CycleKey key(nsteps, o->cgs_refine, from_rhs ? 1 : 0, (const void *)e->Wb[0], (const void *)peer_lo, (const void *)peer_hi);
+      auto itg = e->cycle_graphs.find(key);
+      if (itg == e->cycle_graphs.end()) {
+        const int64_t l0 = e->launches;
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_cycle();
+        cudaError_t ce = cudaStreamEndCapture(e->st, &graph);
+        if (rc || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (!rc) MSP_FAIL(std::string("stream capture failed: ") + cudaGetErrorString(ce)); return rc; }
+        msp_engine::CycleGraph cg{nullptr, (int)(e->launches - l0)};
+        e->launches = l0;
+        ce = cudaGraphInstantiate(&cg.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) MSP_FAIL(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+        if (e->cycle_graphs.size() > 256) { for (auto &kv : e->cycle_graphs) cudaGraphExecDestroy(kv.second.exec); e->cycle_graphs.clear(); }
+        itg = e->cycle_graphs.emplace(key, cg).first;
+      }
+      CK(cudaGraphLaunch(itg->second.exec, e->st));
+      e->launches += itg->second.launches;
     } else {
-      SpmvArgs a = spmv_args(e, e->x, e->Wb[0]);
-      a.b = e->rhs;
-      launch_spmv_w<0, true, false, true>(e, a, 0, e->ctl);
+      RC(enqueue_cycle());
     }
     first = false;
-    const int nsteps = std::min(o->restart, o->max_it - itcount);
-    int cur = 0; // Wb[cur] holds the un-normalised new basis vector
-    for (int it = 0; it < nsteps; it++) {
-      // v_it = w/||w|| (deferred VecNormalize, K5) fused with w' = A v_it (K1)
-      SpmvArgs a = spmv_args(e, e->Wb[cur], e->Wb[cur ^ 1]);
-      a.vout = e->V + (long long)it * e->ld; a.guard_it = it;
-      launch_spmv_w<0, false, true, false>(e, a, 0, nullptr);
-      cur ^= 1;
-      // classical Gram-Schmidt: lhh = -V^T w (K3); w += V lhh, ||w|| (K4+K5), Hessenberg + test (K6)
-      launch_mdot(e, it + 1, e->V, e->ld, e->Wb[cur], reinterpret_cast<double *>(reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, lhh)),
-                  -1.0, it, 0);
-      launch_maxpy<1>(e, it + 1, e->V, e->ld, reinterpret_cast<double *>(reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, lhh)),
-                      e->Wb[cur], nullptr, it, 0, 0, 0);
-      if (o->cgs_refine) {
-        launch_mdot(e, it + 1, e->V, e->ld, e->Wb[cur],
-                    reinterpret_cast<double *>(reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, lhh)), -1.0, it, 1);
-        launch_maxpy<1>(e, it + 1, e->V, e->ld, reinterpret_cast<double *>(reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, lhh)),
-                        e->Wb[cur], nullptr, it, 1, 1, 0);
-      }
-    }
-    // ---- KSPGMRESBuildSoln + boundary publication ----
-    k_build_soln_coef<<<1, 32, 0, e->st>>>(e->ctl);
-    UpdateXArgs u{};
-    u.nb = e->nb; u.H = e->H; u.ld = e->ld; u.V = e->V; u.x = e->x; u.ctl = e->ctl; u.peer_lo = peer_lo; u.peer_hi = peer_hi;
-    k_update_x<<<grid_for(e->nb, 8), MSPK_THREADS, 0, e->st>>>(u);
-    e->launches += 2;
-    CK(cudaMemcpyAsync(e->hsc + 32, reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, its), 16, cudaMemcpyDeviceToHost, e->st));
     CK(cudaStreamSynchronize(e->st));
     memcpy(&hc, e->hsc + 32, 16);
-    // swap roles: after the cycle Wb[cur] is free again; keep Wb[0] as the prologue target
-    if (cur != 0) std::swap(e->Wb[0], e->Wb[1]);
     itcount += hc.it;
     if (hc.reason) break;
     if (itcount >= o->max_it) { hc.reason = MSP_DIVERGED_ITS; break; }
