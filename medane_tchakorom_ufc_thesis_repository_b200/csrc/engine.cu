@@ -311,7 +311,7 @@ static int set_device(int device) {
 template <int MODE, bool RESID, bool SCALE, bool NORM>
 static void launch_spmv_w(msp_engine *e, const SpmvArgs &a, int ws_slot, GmresCtl *ctl_rw) {
   const int g = grid_for(((long long)a.nb + 1) / 2, 8);
-  e->prof_begin(0, 12.0 * (double)e->nnz + 4.0 * (e->nb + 1) + 16.0 * e->nb + (SCALE ? 8.0 * e->nb : 0.0) + (RESID ? 8.0 * e->nb : 0.0));
+  e->prof_begin(0, 12.0 * (double)e->nnz + 4.0 * (e->nb + 1) + 16.0 * e->nb + (RESID ? 8.0 * e->nb : 0.0));
   if (a.W == 5) k_spmv_ell<5, MODE, RESID, SCALE, NORM><<<g, MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
   else if (a.W == 7) k_spmv_ell<7, MODE, RESID, SCALE, NORM><<<g, MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
   else k_spmv_ell<0, MODE, RESID, SCALE, NORM><<<g, MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
@@ -322,14 +322,14 @@ static void launch_spmv_w(msp_engine *e, const SpmvArgs &a, int ws_slot, GmresCt
 static SpmvArgs spmv_args(msp_engine *e, const double *x, double *y) {
   SpmvArgs a{};
   a.nb = e->nb; a.W = e->W; a.H = e->H; a.ld = e->ld; a.ecol = e->ecol; a.eval = e->eval;
-  a.x = x; a.y = y; a.lo = nullptr; a.hi = nullptr; a.b = nullptr; a.vout = nullptr; a.ctl = e->ctl; a.guard_it = -1;
+  a.x = x; a.y = y; a.lo = nullptr; a.hi = nullptr; a.b = nullptr; a.ctl = e->ctl; a.guard_it = -1;
   return a;
 }
 
 static void launch_mdot(msp_engine *e, int nv, const double *V, long long ldv, const double *w, double *h, double sign, int guard_it,
-                        int guard_refine) {
+                        int guard_refine, const double *inv = nullptr) {
   MdotArgs a{};
-  a.nb = e->nb; a.nv = nv; a.ld = ldv; a.V = V; a.w = w; a.h = h; a.sign = sign; a.ctl = e->ctl;
+  a.nb = e->nb; a.nv = nv; a.ld = ldv; a.V = V; a.w = w; a.h = h; a.sign = sign; a.ctl = e->ctl; a.inv = inv;
   a.guard_it = guard_it; a.guard_refine = guard_refine;
   int ngroups = (nv + 7) / 8;
   a.per_group = (nv + ngroups - 1) / ngroups;
@@ -352,9 +352,9 @@ static void launch_mdot(msp_engine *e, int nv, const double *V, long long ldv, c
 
 template <int FIN>
 static void launch_maxpy(msp_engine *e, int nv, const double *V, long long ldv, const double *coef, double *w, double *norm_out,
-                         int guard_it, int guard_refine, int pass, int ws_slot) {
+                         int guard_it, int guard_refine, int pass, int ws_slot, const double *inv = nullptr) {
   MaxpyArgs a{};
-  a.nb = e->nb; a.nv = nv; a.ld = ldv; a.V = V; a.coef = coef; a.w = w; a.norm_out = norm_out; a.ctl = e->ctl;
+  a.nb = e->nb; a.nv = nv; a.ld = ldv; a.V = V; a.coef = coef; a.w = w; a.norm_out = norm_out; a.ctl = e->ctl; a.inv = inv;
   a.guard_it = guard_it; a.guard_refine = guard_refine; a.pass = pass; a.last_pass = 1;
   e->prof_begin(2, 8.0 * e->nb * (nv + 2));
   k_maxpy_norm<FIN><<<grid_for((long long)e->nb / 4, 8), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot);
@@ -552,31 +552,35 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
     const bool from_rhs = first && guess_zero;
     // everything one restart cycle enqueues: prologue, nsteps Arnoldi steps, solution update, 16-byte status read-back
     auto enqueue_cycle = [&]() -> int {
-      // ---- cycle prologue: r = rhs - A x (or r = rhs), ||r|| and the cycle-begin logic on the device ----
+      // The Krylov basis is stored UN-normalised: vtilde_0 = r, vtilde_(it+1) = orthogonalised A v_it, with
+      // v_j = vtilde_j * inv_arr[j] applied on the fly by every consumer (rounded exactly as a stored
+      // normalised vector would be).  This removes VecNormalize's write pass (K5) and the scratch vectors.
+      // ---- cycle prologue: vtilde_0 = rhs - A x (or rhs), ||r|| and the cycle-begin logic on the device ----
+      double *V0 = e->V;
       if (from_rhs) {
-        k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, e->rhs, e->Wb[0]);
+        k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, e->rhs, V0);
         k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->rhs, 0.0, e->ws, 2, e->dsc + 9);
         k_ctl_cycle_begin_from<<<1, 32, 0, e->st>>>(e->ctl, e->dsc + 9);
         e->launches += 3;
       } else {
-        SpmvArgs a = spmv_args(e, e->x, e->Wb[0]);
+        SpmvArgs a = spmv_args(e, e->x, V0);
         a.b = e->rhs;
         launch_spmv_w<0, true, false, true>(e, a, 0, e->ctl);
       }
-      int cur = 0; // Wb[cur] holds the un-normalised new basis vector
       double *lhh = reinterpret_cast<double *>(reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, lhh));
+      const double *invs = reinterpret_cast<const double *>(reinterpret_cast<const char *>(e->ctl) + offsetof(GmresCtl, inv_arr));
       for (int it = 0; it < nsteps; it++) {
-        // v_it = w/||w|| (deferred VecNormalize, K5) fused with w' = A v_it (K1)
-        SpmvArgs a = spmv_args(e, e->Wb[cur], e->Wb[cur ^ 1]);
-        a.vout = e->V + (long long)it * e->ld; a.guard_it = it;
+        // w = A v_it (K1), reading vtilde_it scaled on the fly, written straight into the slot of vtilde_(it+1)
+        double *w = e->V + (long long)(it + 1) * e->ld;
+        SpmvArgs a = spmv_args(e, e->V + (long long)it * e->ld, w);
+        a.guard_it = it;
         launch_spmv_w<0, false, true, false>(e, a, 0, nullptr);
-        cur ^= 1;
         // classical Gram-Schmidt: lhh = -V^T w (K3); w += V lhh, ||w|| (K4+K5), Hessenberg + test (K6)
-        launch_mdot(e, it + 1, e->V, e->ld, e->Wb[cur], lhh, -1.0, it, 0);
-        launch_maxpy<1>(e, it + 1, e->V, e->ld, lhh, e->Wb[cur], nullptr, it, 0, 0, 0);
+        launch_mdot(e, it + 1, e->V, e->ld, w, lhh, -1.0, it, 0, invs);
+        launch_maxpy<1>(e, it + 1, e->V, e->ld, lhh, w, nullptr, it, 0, 0, 0, invs);
         if (o->cgs_refine) {
-          launch_mdot(e, it + 1, e->V, e->ld, e->Wb[cur], lhh, -1.0, it, 1);
-          launch_maxpy<1>(e, it + 1, e->V, e->ld, lhh, e->Wb[cur], nullptr, it, 1, 1, 0);
+          launch_mdot(e, it + 1, e->V, e->ld, w, lhh, -1.0, it, 1, invs);
+          launch_maxpy<1>(e, it + 1, e->V, e->ld, lhh, w, nullptr, it, 1, 1, 0, invs);
         }
       }
       // ---- KSPGMRESBuildSoln + boundary publication ----
@@ -589,7 +593,7 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
       return 0;
     };
     if (e->use_graphs && !e->prof) {
-      const msp_engine::CycleKey key(nsteps, o->cgs_refine, from_rhs ? 1 : 0, (const void *)e->Wb[0], (const void *)peer_lo, (const void *)peer_hi);
+      const msp_engine::CycleKey key(nsteps, o->cgs_refine, from_rhs ? 1 : 0, (const void *)e->V, (const void *)peer_lo, (const void *)peer_hi);
       auto itg = e->cycle_graphs.find(key);
       if (itg == e->cycle_graphs.end()) {
         const int64_t l0 = e->launches;
@@ -1285,7 +1289,7 @@ int msp_bench_kernel(msp_engine *e, int op, int nv, int iters, int flush_l2, dou
       case 2: launch_maxpy<0>(e, nv, e->V, e->ld, e->dsc + 64, e->Wb[0], e->dsc + 200, -1, 0, 0, 3); break;
       case 3: RC(op_spmm(e, MSP_ALG_SMSM_GLOBAL, nv)); break;
       case 4: k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, e->Wb[0], e->Wb[1]); break;
-      case 5: { SpmvArgs a = spmv_args(e, e->Wb[0], e->Wb[1]); a.vout = e->V; launch_spmv_w<0, false, true, false>(e, a, 0, nullptr); break; }
+      case 5: { SpmvArgs a = spmv_args(e, e->Wb[0], e->Wb[1]); launch_spmv_w<0, false, true, false>(e, a, 0, nullptr); break; }
       default: MSP_FAIL("unknown op");
     }
     CK(cudaEventRecord(e1, e->st));

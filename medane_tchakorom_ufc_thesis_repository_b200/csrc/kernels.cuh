@@ -38,7 +38,8 @@ struct GmresCtl {
   double ksp_rnorm;
   double gm_rnorm0; // residual at the start of the cycle
   double rnorm0, ttol; // KSPConvergedDefault context
-  double inv;      // 1/norm for the deferred VecNormalize
+  double inv;      // 1/norm of the newest basis vector
+  double inv_arr[MSPK_MAXK + 2]; // 1/||w_j||: the basis is stored un-normalised, v_j = vtilde_j * inv_arr[j] on the fly
   double tt;       // last norm
   double grs[MSPK_MAXK + 2], cc[MSPK_MAXK + 2], ss[MSPK_MAXK + 2];
   double lhh[MSPK_MAXK + 2];  // MDot result of the current step (pass 0 / pass 1)
@@ -113,6 +114,7 @@ __device__ inline void ctl_cycle_begin(GmresCtl *c, double res) {
   c->refine = 0;
   c->tt = res;
   c->inv = (res > 0.0) ? 1.0 / res : 0.0;
+  c->inv_arr[0] = c->inv;
   if (isnan(res) || isinf(res)) { c->reason = -9; c->active = 0; return; }
   if (!c->first_cycle && c->ksp_rnorm > 0.0 && fabs(res - c->ksp_rnorm) > 0.1 * c->gm_rnorm0) {
     c->reason = -5; c->active = 0; return;
@@ -135,6 +137,7 @@ __device__ inline void ctl_step_end(GmresCtl *c, double tt) {
   double *hh = &c->hh[(size_t)it * ld];
   c->tt = tt;
   c->inv = (tt > 0.0) ? 1.0 / tt : 0.0;
+  c->inv_arr[it + 1] = c->inv;
   if (isnan(tt) || isinf(tt)) { c->reason = -9; c->active = 0; return; }
   hh[it + 1] = tt;
   double hapbnd = fabs(tt / c->grs[it]);
@@ -278,8 +281,7 @@ struct SpmvArgs {
   const double *lo, *hi; // neighbour boundaries (MODE 1), may be null
   const double *b;      // RESID: y = b - A x
   double *y;
-  double *vout;         // SCALE: vout = x * inv (own rows)
-  const GmresCtl *ctl;  // SCALE: inv = ctl->inv ; guards
+  const GmresCtl *ctl;  // SCALE: input is the un-normalised basis vector, inv = ctl->inv_arr[max(guard_it, 0)] ; guards
   int guard_it;         // run only if ctl->active && ctl->it == guard_it  (-1: always)
 };
 
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_spmv_ell(SpmvArgs a, ReduceWs 
     if (!a.ctl->active || a.ctl->it != a.guard_it) return;
   }
   const int W = (W_T > 0) ? W_T : a.W;
-  const double inv = SCALE ? a.ctl->inv : 1.0;
+  const double inv = SCALE ? a.ctl->inv_arr[a.guard_it > 0 ? a.guard_it : 0] : 1.0;
   double nrm = 0.0;
   const long long npairs = (a.nb + 1) >> 1;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npairs; p += (long long)gridDim.x * blockDim.x) {
@@ -322,14 +324,9 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_spmv_ell(SpmvArgs a, ReduceWs 
     }
     if (r + 1 < a.nb) {
       *reinterpret_cast<double2 *>(a.y + r) = make_double2(s0, s1);
-      if (SCALE) {
-        const double2 w = *reinterpret_cast<const double2 *>(a.x + r);
-        *reinterpret_cast<double2 *>(a.vout + r) = make_double2(w.x * inv, w.y * inv);
-      }
       if (NORM) nrm = fma(s0, s0, fma(s1, s1, nrm));
     } else {
       a.y[r] = s0;
-      if (SCALE) a.vout[r] = a.x[r] * inv;
       if (NORM) nrm = fma(s0, s0, nrm);
     }
   }
@@ -368,6 +365,7 @@ struct MdotArgs {
   const double *V;     // basis, vector j at V + j*ld
   const double *w;
   double *h;           // result (device); written as sign * dot
+  const double *inv;   // per-vector scale of the stored (un-normalised) basis, or null
   double sign;         // -1: PETSc's lhh = -<w, v>
   const GmresCtl *ctl;
   int guard_it, guard_refine; // guard_refine: run only if ctl->refine (second CGS pass)
@@ -383,9 +381,10 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_mdot(MdotArgs a, ReduceWs ws) 
   const int v0 = g * a.per_group;
   const int nv = min(a.per_group, a.nv - v0);
   const double *Vg = a.V + (long long)v0 * a.ld;
-  double acc[NVMAX];
+  double acc[NVMAX], iv[NVMAX];
 #pragma unroll
-  for (int v = 0; v < NVMAX; v++) acc[v] = 0.0;
+  for (int v = 0; v < NVMAX; v++) { acc[v] = 0.0; iv[v] = (a.inv && v < nv) ? a.inv[v0 + v] : 1.0; }
+  const bool scaled = a.inv != nullptr;
   const long long npairs = a.nb >> 1;
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -405,8 +404,10 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_mdot(MdotArgs a, ReduceWs ws) 
       if (v < nv) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          acc[v] = fma(x[u][v].x, w[u].x, acc[v]);
-          acc[v] = fma(x[u][v].y, w[u].y, acc[v]);
+          // v_j = vtilde_j * inv_j, rounded exactly like the stored normalised vector would have been
+          const double vx = scaled ? x[u][v].x * iv[v] : x[u][v].x, vy = scaled ? x[u][v].y * iv[v] : x[u][v].y;
+          acc[v] = fma(vx, w[u].x, acc[v]);
+          acc[v] = fma(vy, w[u].y, acc[v]);
         }
       }
   }
@@ -416,15 +417,16 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_mdot(MdotArgs a, ReduceWs ws) 
     for (int v = 0; v < NVMAX; v++)
       if (v < nv) {
         const double2 x0 = ld_stream2(Vg + v * a.ld + 2 * p);
-        acc[v] = fma(x0.x, w0.x, acc[v]);
-        acc[v] = fma(x0.y, w0.y, acc[v]);
+        const double vx = scaled ? x0.x * iv[v] : x0.x, vy = scaled ? x0.y * iv[v] : x0.y;
+        acc[v] = fma(vx, w0.x, acc[v]);
+        acc[v] = fma(vy, w0.y, acc[v]);
       }
   }
   if ((a.nb & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const double wl = a.w[a.nb - 1];
 #pragma unroll
     for (int v = 0; v < NVMAX; v++)
-      if (v < nv) acc[v] = fma(Vg[v * a.ld + a.nb - 1], wl, acc[v]);
+      if (v < nv) { const double xv = Vg[v * a.ld + a.nb - 1]; acc[v] = fma(scaled ? xv * iv[v] : xv, wl, acc[v]); }
   }
   __shared__ double sm[32];
   __shared__ bool last;
@@ -464,6 +466,7 @@ struct MaxpyArgs {
   long long ld;
   const double *V;
   const double *coef;  // device, nv coefficients
+  const double *inv;   // per-vector scale of the stored (un-normalised) basis, or null
   double *w;
   double *norm_out;    // device scalar (may be null)
   GmresCtl *ctl;
@@ -478,9 +481,10 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
     if (!a.ctl->active || a.ctl->it != a.guard_it) return;
     if (a.guard_refine && !a.ctl->refine) return;
   }
-  __shared__ double cf[MSPK_MAXK + 2];
-  for (int j = threadIdx.x; j < a.nv; j += blockDim.x) cf[j] = a.coef[j];
+  __shared__ double cf[MSPK_MAXK + 2], sc[MSPK_MAXK + 2];
+  for (int j = threadIdx.x; j < a.nv; j += blockDim.x) { cf[j] = a.coef[j]; sc[j] = a.inv ? a.inv[j] : 1.0; }
   __syncthreads();
+  const bool scaled = a.inv != nullptr;
   double nrm = 0.0;
   const long long npairs = a.nb >> 1;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -500,6 +504,7 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         const double c = cf[j + u];
+        if (scaled) { const double q = sc[j + u]; x0[u].x *= q; x0[u].y *= q; x1[u].x *= q; x1[u].y *= q; }
         t0.x = fma(c, x0[u].x, t0.x); t0.y = fma(c, x0[u].y, t0.y);
         t1.x = fma(c, x1[u].x, t1.x); t1.y = fma(c, x1[u].y, t1.y);
       }
@@ -516,6 +521,7 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
       for (int u = 0; u < 8; u++)
         if (j + u < a.nv) {
           const double c = cf[j + u];
+          if (scaled) { const double q = sc[j + u]; x0[u].x *= q; x0[u].y *= q; x1[u].x *= q; x1[u].y *= q; }
           t0.x = fma(c, x0[u].x, t0.x); t0.y = fma(c, x0[u].y, t0.y);
           t1.x = fma(c, x1[u].x, t1.x); t1.y = fma(c, x1[u].y, t1.y);
         }
@@ -528,7 +534,8 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
   for (; p < npairs; p += stride) {
     double2 t = *reinterpret_cast<const double2 *>(a.w + 2 * p);
     for (int j = 0; j < a.nv; j++) {
-      const double2 x = ld_stream2(a.V + (long long)j * a.ld + 2 * p);
+      double2 x = ld_stream2(a.V + (long long)j * a.ld + 2 * p);
+      if (scaled) { x.x *= sc[j]; x.y *= sc[j]; }
       t.x = fma(cf[j], x.x, t.x); t.y = fma(cf[j], x.y, t.y);
     }
     *reinterpret_cast<double2 *>(a.w + 2 * p) = t;
@@ -536,7 +543,7 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
   }
   if ((a.nb & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     double t = a.w[a.nb - 1];
-    for (int j = 0; j < a.nv; j++) t = fma(cf[j], a.V[(long long)j * a.ld + a.nb - 1], t);
+    for (int j = 0; j < a.nv; j++) { const double xv = a.V[(long long)j * a.ld + a.nb - 1]; t = fma(cf[j], scaled ? xv * sc[j] : xv, t); }
     a.w[a.nb - 1] = t;
     nrm = fma(t, t, nrm);
   }
@@ -617,8 +624,8 @@ struct UpdateXArgs {
 
 __global__ void __launch_bounds__(MSPK_THREADS) k_update_x(UpdateXArgs a) {
   const int nv = a.ctl->it;
-  __shared__ double cf[MSPK_MAXK + 2];
-  for (int j = threadIdx.x; j < nv; j += blockDim.x) cf[j] = a.ctl->nrs[j];
+  __shared__ double cf[MSPK_MAXK + 2], sc[MSPK_MAXK + 2];
+  for (int j = threadIdx.x; j < nv; j += blockDim.x) { cf[j] = a.ctl->nrs[j]; sc[j] = a.ctl->inv_arr[j]; }
   __syncthreads();
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < a.nb; r += (long long)gridDim.x * blockDim.x) {
     double xv = a.x[r];
@@ -631,9 +638,9 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_update_x(UpdateXArgs a) {
 #pragma unroll
         for (int u = 0; u < 8; u++) v[u] = __ldg(a.V + (long long)(j + u) * a.ld + r);
 #pragma unroll
-        for (int u = 0; u < 8; u++) t = fma(cf[j + u], v[u], t);
+        for (int u = 0; u < 8; u++) t = fma(cf[j + u], v[u] * sc[j + u], t);
       }
-      for (; j < nv; j++) t = fma(cf[j], __ldg(a.V + (long long)j * a.ld + r), t);
+      for (; j < nv; j++) t = fma(cf[j], __ldg(a.V + (long long)j * a.ld + r) * sc[j], t);
       xv = xv + t;
       a.x[r] = xv;
     }
