@@ -553,8 +553,9 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
     // everything one restart cycle enqueues: prologue, nsteps Arnoldi steps, solution update, 16-byte status read-back
     auto enqueue_cycle = [&]() -> int {
       // The Krylov basis is stored UN-normalised: vtilde_0 = r, vtilde_(it+1) = orthogonalised A v_it, with
-      // v_j = vtilde_j * inv_arr[j] applied on the fly by every consumer (rounded exactly as a stored
-      // normalised vector would be).  This removes VecNormalize's write pass (K5) and the scratch vectors.
+      // v_j = vtilde_j * inv_arr[j]: the SpMV scales its gathered input (bit-identical to a stored normalised vector),
+      // MDot scales the reduced value and MAXPY / the solution update fold inv_j into their coefficients.  This
+      // removes VecNormalize's write pass (K5) and the scratch vectors from the Arnoldi step.
       // ---- cycle prologue: vtilde_0 = rhs - A x (or rhs), ||r|| and the cycle-begin logic on the device ----
       double *V0 = e->V;
       if (from_rhs) {

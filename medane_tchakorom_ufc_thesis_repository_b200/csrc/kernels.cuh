@@ -381,10 +381,9 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_mdot(MdotArgs a, ReduceWs ws) 
   const int v0 = g * a.per_group;
   const int nv = min(a.per_group, a.nv - v0);
   const double *Vg = a.V + (long long)v0 * a.ld;
-  double acc[NVMAX], iv[NVMAX];
+  double acc[NVMAX];
 #pragma unroll
-  for (int v = 0; v < NVMAX; v++) { acc[v] = 0.0; iv[v] = (a.inv && v < nv) ? a.inv[v0 + v] : 1.0; }
-  const bool scaled = a.inv != nullptr;
+  for (int v = 0; v < NVMAX; v++) acc[v] = 0.0;
   const long long npairs = a.nb >> 1;
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -404,10 +403,8 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_mdot(MdotArgs a, ReduceWs ws) 
       if (v < nv) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          // v_j = vtilde_j * inv_j, rounded exactly like the stored normalised vector would have been
-          const double vx = scaled ? x[u][v].x * iv[v] : x[u][v].x, vy = scaled ? x[u][v].y * iv[v] : x[u][v].y;
-          acc[v] = fma(vx, w[u].x, acc[v]);
-          acc[v] = fma(vy, w[u].y, acc[v]);
+          acc[v] = fma(x[u][v].x, w[u].x, acc[v]);
+          acc[v] = fma(x[u][v].y, w[u].y, acc[v]);
         }
       }
   }
@@ -417,16 +414,15 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_mdot(MdotArgs a, ReduceWs ws) 
     for (int v = 0; v < NVMAX; v++)
       if (v < nv) {
         const double2 x0 = ld_stream2(Vg + v * a.ld + 2 * p);
-        const double vx = scaled ? x0.x * iv[v] : x0.x, vy = scaled ? x0.y * iv[v] : x0.y;
-        acc[v] = fma(vx, w0.x, acc[v]);
-        acc[v] = fma(vy, w0.y, acc[v]);
+        acc[v] = fma(x0.x, w0.x, acc[v]);
+        acc[v] = fma(x0.y, w0.y, acc[v]);
       }
   }
   if ((a.nb & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const double wl = a.w[a.nb - 1];
 #pragma unroll
     for (int v = 0; v < NVMAX; v++)
-      if (v < nv) { const double xv = Vg[v * a.ld + a.nb - 1]; acc[v] = fma(scaled ? xv * iv[v] : xv, wl, acc[v]); }
+      if (v < nv) acc[v] = fma(Vg[v * a.ld + a.nb - 1], wl, acc[v]);
   }
   __shared__ double sm[32];
   __shared__ bool last;
@@ -449,7 +445,8 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_mdot(MdotArgs a, ReduceWs ws) 
       double s = 0.0;
       for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += __ldcg(ws.partial + (slot * 8 + v) * (long long)MSPK_MAX_PART + i);
       double tot = block_sum(s, sm);
-      if (threadIdx.x == 0) a.h[v0 + v] = a.sign * tot;
+      // <w, v_j> = inv_j <w, vtilde_j>: the scale of the un-normalised basis vector is applied to the reduced value
+      if (threadIdx.x == 0) a.h[v0 + v] = a.sign * (a.inv ? tot * a.inv[v0 + v] : tot);
     }
     if (threadIdx.x == 0) ws.counter[slot] = 0;
   }
@@ -481,10 +478,10 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
     if (!a.ctl->active || a.ctl->it != a.guard_it) return;
     if (a.guard_refine && !a.ctl->refine) return;
   }
-  __shared__ double cf[MSPK_MAXK + 2], sc[MSPK_MAXK + 2];
-  for (int j = threadIdx.x; j < a.nv; j += blockDim.x) { cf[j] = a.coef[j]; sc[j] = a.inv ? a.inv[j] : 1.0; }
+  __shared__ double cf[MSPK_MAXK + 2];
+  // w += sum_j coef_j v_j with v_j = inv_j vtilde_j: the scale is folded into the coefficient
+  for (int j = threadIdx.x; j < a.nv; j += blockDim.x) cf[j] = a.inv ? a.coef[j] * a.inv[j] : a.coef[j];
   __syncthreads();
-  const bool scaled = a.inv != nullptr;
   double nrm = 0.0;
   const long long npairs = a.nb >> 1;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -504,7 +501,6 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         const double c = cf[j + u];
-        if (scaled) { const double q = sc[j + u]; x0[u].x *= q; x0[u].y *= q; x1[u].x *= q; x1[u].y *= q; }
         t0.x = fma(c, x0[u].x, t0.x); t0.y = fma(c, x0[u].y, t0.y);
         t1.x = fma(c, x1[u].x, t1.x); t1.y = fma(c, x1[u].y, t1.y);
       }
@@ -521,8 +517,7 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
       for (int u = 0; u < 8; u++)
         if (j + u < a.nv) {
           const double c = cf[j + u];
-          if (scaled) { const double q = sc[j + u]; x0[u].x *= q; x0[u].y *= q; x1[u].x *= q; x1[u].y *= q; }
-          t0.x = fma(c, x0[u].x, t0.x); t0.y = fma(c, x0[u].y, t0.y);
+            t0.x = fma(c, x0[u].x, t0.x); t0.y = fma(c, x0[u].y, t0.y);
           t1.x = fma(c, x1[u].x, t1.x); t1.y = fma(c, x1[u].y, t1.y);
         }
     }
@@ -534,8 +529,7 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
   for (; p < npairs; p += stride) {
     double2 t = *reinterpret_cast<const double2 *>(a.w + 2 * p);
     for (int j = 0; j < a.nv; j++) {
-      double2 x = ld_stream2(a.V + (long long)j * a.ld + 2 * p);
-      if (scaled) { x.x *= sc[j]; x.y *= sc[j]; }
+      const double2 x = ld_stream2(a.V + (long long)j * a.ld + 2 * p);
       t.x = fma(cf[j], x.x, t.x); t.y = fma(cf[j], x.y, t.y);
     }
     *reinterpret_cast<double2 *>(a.w + 2 * p) = t;
@@ -543,7 +537,7 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
   }
   if ((a.nb & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     double t = a.w[a.nb - 1];
-    for (int j = 0; j < a.nv; j++) { const double xv = a.V[(long long)j * a.ld + a.nb - 1]; t = fma(cf[j], scaled ? xv * sc[j] : xv, t); }
+    for (int j = 0; j < a.nv; j++) t = fma(cf[j], a.V[(long long)j * a.ld + a.nb - 1], t);
     a.w[a.nb - 1] = t;
     nrm = fma(t, t, nrm);
   }
@@ -624,8 +618,8 @@ struct UpdateXArgs {
 
 __global__ void __launch_bounds__(MSPK_THREADS) k_update_x(UpdateXArgs a) {
   const int nv = a.ctl->it;
-  __shared__ double cf[MSPK_MAXK + 2], sc[MSPK_MAXK + 2];
-  for (int j = threadIdx.x; j < nv; j += blockDim.x) { cf[j] = a.ctl->nrs[j]; sc[j] = a.ctl->inv_arr[j]; }
+  __shared__ double cf[MSPK_MAXK + 2];
+  for (int j = threadIdx.x; j < nv; j += blockDim.x) cf[j] = a.ctl->nrs[j] * a.ctl->inv_arr[j];
   __syncthreads();
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < a.nb; r += (long long)gridDim.x * blockDim.x) {
     double xv = a.x[r];
@@ -638,9 +632,9 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_update_x(UpdateXArgs a) {
 #pragma unroll
         for (int u = 0; u < 8; u++) v[u] = __ldg(a.V + (long long)(j + u) * a.ld + r);
 #pragma unroll
-        for (int u = 0; u < 8; u++) t = fma(cf[j + u], v[u] * sc[j + u], t);
+        for (int u = 0; u < 8; u++) t = fma(cf[j + u], v[u], t);
       }
-      for (; j < nv; j++) t = fma(cf[j], __ldg(a.V + (long long)j * a.ld + r) * sc[j], t);
+      for (; j < nv; j++) t = fma(cf[j], __ldg(a.V + (long long)j * a.ld + r), t);
       xv = xv + t;
       a.x[r] = xv;
     }
