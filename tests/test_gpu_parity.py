@@ -255,7 +255,7 @@ def test_sync_driver_parity(S, oracle, g):
     well_conditioned = g["alg"] == "SM" or g["nblocks"] == 1 or g["inner"]["max_it"] <= 5
     assert np.linalg.norm(x - ref["x"]) <= (1e-8 if well_conditioned else 1e-6) * np.linalg.norm(ref["x"])
     # semi-local / local: every block reports its own local norm; the oracle's history keeps the worst block
-    assert np.allclose(np.max([r["hist"] for r in res], axis=0), ref["hist"], rtol=1e-6)
+    assert np.allclose(np.max([r["hist"] for r in res], axis=0), ref["hist"], rtol=1e-6 if well_conditioned else 1e-2)
     assert abs(res[0]["norm0"] - g["norm0"]) <= 1e-13 * g["norm0"]
     grp.close()
     # (b)
