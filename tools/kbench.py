@@ -35,7 +35,7 @@ def rec(name, ms, bytes_):
 rec("copy (STREAM)", e.bench_kernel(4, iters=20), 16 * n)
 rec("spmv ELL  [CSR bytes]", e.bench_kernel(0, iters=20), 12 * nnz + 4 * (n + 1) + 16 * n)
 ms = e.bench_kernel(5, iters=20)
-rec("scale+spmv [CSR bytes+16n]", ms, 12 * nnz + 4 * (n + 1) + 16 * n + 16 * n)
+rec("spmv, input scaled on the fly", ms, 12 * nnz + 4 * (n + 1) + 16 * n)
 for nv in (1, 2, 4, 8, 9, 16, 24, 30):
     if nv > restart:
         continue
