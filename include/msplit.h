@@ -61,7 +61,7 @@ typedef struct {
   int initial_rtol;  /* -ksp_converged_use_initial_residual_norm / KSPConvergedDefaultSetUIRNorm */
   int guess_nonzero; /* KSPSetInitialGuessNonzero */
   int cgs_refine;    /* -ksp_gmres_cgs_refinement_type: 0 never, 1 ifneeded, 2 always */
-  int mgs;           /* -ksp_gmres_modifiedgramschmidt (not supported on the device path: error) */
+  int mgs;           /* -ksp_gmres_modifiedgramschmidt */
   int min_it;        /* 0 */
 } msp_ksp_opts;
 
@@ -83,6 +83,12 @@ typedef struct {
   int max_outer;        /* safety cap (reference: none); 0 = 1000000 */
   int record_history;
   int profile;          /* bracket every hot-kernel launch with CUDA events and fill the per-class t_, b_ and n_ fields */
+  /* minimiser (outer_solver_norm_equation utils.c:1061-1103): 0 = exact least squares by TSQR (default),
+   * 1 = PETSc-faithful LSQR on R with zero initial guess and the initial-residual-norm test, as every shipped
+   * command line selects (-outer{K}_ksp_type lsqr -outer{K}_ksp_max_it 40..200 -outer{K}_ksp_rtol 1e-14..1e-50) */
+  int outer_type;
+  int outer_max_it;
+  double outer_rtol, outer_abstol;
   /* async emulation in one process: block K runs a step at tick t iff t % period[K] == 0 */
   int period[MSP_MAX_BLOCKS];
 } msp_solve_opts;
@@ -104,6 +110,10 @@ typedef struct {
   double t_spmv_ms, t_mdot_ms, t_maxpy_ms, t_other_ms;
   double b_spmv, b_mdot, b_maxpy, b_other;   /* algorithmic bytes moved by each class (SURVEY.md §8d formulas) */
   int64_t n_spmv, n_mdot, n_maxpy, n_other;  /* launches per class */
+  /* the reference's PetscLogStage split (…-global.c:81-89): host time spent in the inner solves ("I_Solver stage")
+   * and in the exchange + minimisation + convergence test ("O_Solver stage") */
+  double stage_inner_s, stage_outer_s;
+  int64_t outer_solver_its;   /* LSQR iterations summed over the outer iterations (0 with TSQR) */
 } msp_result;
 
 int msp_version(void);

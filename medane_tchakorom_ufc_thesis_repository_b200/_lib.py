@@ -38,7 +38,8 @@ class Problem(C.Structure):
 class SolveOpts(C.Structure):
     _fields_ = [
         ("alg", C.c_int), ("s", C.c_int), ("rtol", C.c_double), ("inner", KspOpts), ("max_outer", C.c_int),
-        ("record_history", C.c_int), ("profile", C.c_int), ("period", C.c_int * MAX_BLOCKS),
+        ("record_history", C.c_int), ("profile", C.c_int), ("outer_type", C.c_int), ("outer_max_it", C.c_int),
+        ("outer_rtol", C.c_double), ("outer_abstol", C.c_double), ("period", C.c_int * MAX_BLOCKS),
     ]
 
 
@@ -51,6 +52,7 @@ class Result(C.Structure):
         ("t_spmv_ms", C.c_double), ("t_mdot_ms", C.c_double), ("t_maxpy_ms", C.c_double), ("t_other_ms", C.c_double),
         ("b_spmv", C.c_double), ("b_mdot", C.c_double), ("b_maxpy", C.c_double), ("b_other", C.c_double),
         ("n_spmv", C.c_int64), ("n_mdot", C.c_int64), ("n_maxpy", C.c_int64), ("n_other", C.c_int64),
+        ("stage_inner_s", C.c_double), ("stage_outer_s", C.c_double), ("outer_solver_its", C.c_int64),
     ]
 
     def as_dict(self):
@@ -59,7 +61,8 @@ class Result(C.Structure):
             "last_norm": self.last_norm, "final_residual": self.final_residual, "error": self.error,
             "elapsed_s": self.elapsed_s, "gmres_its": self.gmres_its, "gmres_reason": self.gmres_reason,
             "gmres_rnorm": self.gmres_rnorm, "hist": np.array(self.hist[: self.hist_len]),
-            "kernel_launches": self.kernel_launches,
+            "kernel_launches": self.kernel_launches, "stage_inner_s": self.stage_inner_s,
+            "stage_outer_s": self.stage_outer_s, "outer_solver_its": self.outer_solver_its,
             "prof": {c: {"ms": getattr(self, f"t_{c}_ms"), "bytes": getattr(self, f"b_{c}"), "launches": getattr(self, f"n_{c}")}
                      for c in ("spmv", "mdot", "maxpy", "other")},
         }

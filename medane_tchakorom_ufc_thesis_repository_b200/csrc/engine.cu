@@ -530,7 +530,6 @@ static int read_scalars(msp_engine *e, int first, int n) {
 // inner_solver utils.c:950-970 -> KSPSolve_GMRES.  One host synchronisation per
 // restart cycle; inside a cycle every decision is taken on the device.
 static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, int *its_out, int *reason_out, double *rnorm_out) {
-  if (o->mgs) MSP_FAIL("-ksp_gmres_modifiedgramschmidt is not supported by the device path");
   if (o->restart < 1 || o->restart > e->prob.max_restart) MSP_FAIL("restart exceeds max_restart of the engine");
   const bool guess_zero = !o->guess_nonzero;
   double *bnorm_sq = nullptr;
@@ -576,6 +575,16 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
         SpmvArgs a = spmv_args(e, e->V + (long long)it * e->ld, w);
         a.guard_it = it;
         launch_spmv_w<0, false, true, false>(e, a, 0, nullptr);
+        if (o->mgs) {
+          // -ksp_gmres_modifiedgramschmidt: it+1 sequential (dot, axpy) pairs; the last axpy closes the step
+          for (int j = 0; j <= it; j++) {
+            const double *vj = e->V + (long long)j * e->ld;
+            launch_mdot(e, 1, vj, e->ld, w, lhh + j, -1.0, it, 0, invs + j);
+            if (j < it) launch_maxpy<0>(e, 1, vj, e->ld, lhh + j, w, nullptr, it, 0, 0, 3, invs + j);
+            else launch_maxpy<1>(e, 1, vj, e->ld, lhh + j, w, nullptr, it, 0, 0, 0, invs + j);
+          }
+          continue;
+        }
         // classical Gram-Schmidt: lhh = -V^T w (K3); w += V lhh, ||w|| (K4+K5), Hessenberg + test (K6)
         launch_mdot(e, it + 1, e->V, e->ld, w, lhh, -1.0, it, 0, invs);
         launch_maxpy<1>(e, it + 1, e->V, e->ld, lhh, w, nullptr, it, 0, 0, 0, invs);
@@ -594,7 +603,7 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
       return 0;
     };
     if (e->use_graphs && !e->prof) {
-      const msp_engine::CycleKey key(nsteps, o->cgs_refine, from_rhs ? 1 : 0, (const void *)e->V, (const void *)peer_lo, (const void *)peer_hi);
+      const msp_engine::CycleKey key(nsteps, o->cgs_refine + 4 * (o->mgs ? 1 : 0), from_rhs ? 1 : 0, (const void *)e->V, (const void *)peer_lo, (const void *)peer_hi);
       auto itg = e->cycle_graphs.find(key);
       if (itg == e->cycle_graphs.end()) {
         const int64_t l0 = e->launches;
@@ -662,11 +671,11 @@ static int op_push_iterate(msp_engine *e, int t) {
 // kind: MSP_ALG_*_GLOBAL / SEMI_LOCAL use the strip with stored boundaries, *_LOCAL uses A_KK
 static bool kind_is_local(int kind) { return kind == MSP_ALG_SMSM_LOCAL || kind == MSP_ALG_AMAM_LOCAL; }
 
-static int op_spmm(msp_engine *e, int kind, int s) {
-  // basis of successive corrections (same span as the iterates, far better conditioned)
-  k_diff_basis<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, s, e->ld, e->S);
-  e->launches++;
-  if (!kind_is_local(kind)) {
+static int op_spmm(msp_engine *e, int kind, int s, bool diff_basis = true) {
+  // basis of successive corrections (same span as the iterates, far better conditioned); the LSQR path keeps the
+  // reference's raw basis [x^1 .. x^s]
+  if (diff_basis) { k_diff_basis<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, s, e->ld, e->S); e->launches++; }
+  if (diff_basis && !kind_is_local(kind)) {
     if (e->has_nb[0]) { k_diff_basis<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->H, s, e->H, e->Slo); e->launches++; }
     if (e->has_nb[1]) { k_diff_basis<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->H, s, e->H, e->Shi); e->launches++; }
   }
@@ -737,6 +746,86 @@ static int op_apply_alpha(msp_engine *e, int kind, int s, const double *alpha_ho
         e->launches++;
       }
   }
+  return 0;
+}
+
+static int allreduce_host(msp_engine *e, int first, int n);
+
+// KSPSolve_LSQR (PETSc lsqr.c) on the dense column block R_K (n_K x s) distributed over the blocks:
+// R v and the vector updates are block-local kernels (K10 lincomb, K4 axpy+norm), R^T u is the MDot kernel (K3);
+// with `global` the s-vector R^T u and the two norms of every iteration are summed over blocks (the reference's
+// MatMultTranspose_MPIDense / VecNorm_MPI allreduces).  Zero initial guess, initial-residual-norm test
+// (outer_solver_norm_equation utils.c:1065-1068); returns alpha, phibar and the iteration count.
+static int op_lsqr(msp_engine *e, int kind, int s, bool global, int max_it, double rtol, double abstol, double *alpha, double *rnorm_out,
+                   int *its_out) {
+  const double *rhs_src = kind_is_local(kind) ? e->rhs : e->b;
+  double *U = e->Wb[0], *U1 = e->Wb[1];
+  std::vector<double> V(s, 0.0), V1(s, 0.0), W(s, 0.0);
+  auto sum_blocks = [&](int first, int n) -> int { return global ? allreduce_host(e, first, n) : read_scalars(e, first, n); };
+  auto put_s = [&](const std::vector<double> &v) -> int {
+    memcpy(e->hsc + 216, v.data(), sizeof(double) * s);
+    CK(cudaMemcpyAsync(e->dsc + 216, e->hsc + 216, sizeof(double) * s, cudaMemcpyHostToDevice, e->st));
+    return 0;
+  };
+  for (int j = 0; j < s; j++) alpha[j] = 0.0;
+  k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, rhs_src, U);
+  k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, U, 0.0, e->ws, 2, e->dsc + 4);
+  e->launches += 2;
+  RC(sum_blocks(4, 1));
+  double rnorm = std::sqrt(e->hsc[4]);
+  const double rnorm0 = rnorm, ttol = std::max(rtol * rnorm0, abstol);
+  int its = 0;
+  if (rnorm > 0.0) {
+    double beta = rnorm, al;
+    k_scale<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, 1.0 / beta, U);
+    e->launches++;
+    launch_mdot(e, s, e->R, e->ld, U, e->dsc + 64, 1.0, -1, 0);
+    RC(sum_blocks(64, s));
+    double nv = 0.0;
+    for (int j = 0; j < s; j++) { V[j] = e->hsc[64 + j]; nv += V[j] * V[j]; }
+    al = std::sqrt(nv);
+    if (al > 0.0) for (int j = 0; j < s; j++) V[j] /= al;
+    W = V;
+    double phibar = beta, rhobar = al;
+    int i = 0;
+    do {
+      RC(put_s(V));
+      k_lincomb<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, s, e->ld, e->R, e->dsc + 216, U1); // U1 = R V
+      e->launches++;
+      e->hsc[5] = -al;
+      CK(cudaMemcpyAsync(e->dsc + 5, e->hsc + 5, sizeof(double), cudaMemcpyHostToDevice, e->st));
+      launch_maxpy<0>(e, 1, U, e->ld, e->dsc + 5, U1, e->dsc + 6, -1, 0, 0, 3); // U1 -= alpha U, ||U1||
+      RC(read_scalars(e, 6, 1));
+      e->hsc[6] = e->hsc[6] * e->hsc[6];
+      CK(cudaMemcpyAsync(e->dsc + 6, e->hsc + 6, sizeof(double), cudaMemcpyHostToDevice, e->st));
+      RC(sum_blocks(6, 1));
+      beta = std::sqrt(e->hsc[6]);
+      if (beta > 0.0) { k_scale<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, 1.0 / beta, U1); e->launches++; }
+      launch_mdot(e, s, e->R, e->ld, U1, e->dsc + 64, 1.0, -1, 0); // V1 = R^T U1
+      RC(sum_blocks(64, s));
+      nv = 0.0;
+      for (int j = 0; j < s; j++) { V1[j] = std::fma(-beta, V[j], e->hsc[64 + j]); nv += V1[j] * V1[j]; }
+      al = std::sqrt(nv);
+      if (al > 0.0) for (int j = 0; j < s; j++) V1[j] /= al;
+      const double rho = std::sqrt(rhobar * rhobar + beta * beta);
+      const double c = rhobar / rho, sn = beta / rho, theta = sn * al;
+      rhobar = -c * al;
+      const double phi = c * phibar;
+      phibar = sn * phibar;
+      for (int j = 0; j < s; j++) alpha[j] = std::fma(phi / rho, W[j], alpha[j]);
+      for (int j = 0; j < s; j++) W[j] = V1[j] + (-theta / rho) * W[j];
+      rnorm = phibar;
+      its++;
+      // KSPConvergedDefault with -ksp_convergence_test default (running_bulk_test_g5k:247)
+      bool conv = std::isnan(rnorm) || std::isinf(rnorm) || rnorm <= ttol || rnorm >= 1e4 * rnorm0;
+      if (conv) break;
+      std::swap(U, U1);
+      std::swap(V, V1);
+      i++;
+    } while (i < max_it);
+  }
+  if (rnorm_out) *rnorm_out = rnorm;
+  if (its_out) *its_out = its;
   return 0;
 }
 
@@ -823,12 +912,20 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
   e->prof = o->profile != 0;
   bool done = false;
   int sticky = 0;
+  const bool lsqr = o->outer_type == 1;
+  const int lsqr_max_it = o->outer_max_it > 0 ? o->outer_max_it : 100;
+  const double lsqr_rtol = o->outer_rtol > 0 ? o->outer_rtol : 1e-15, lsqr_abstol = o->outer_abstol > 0 ? o->outer_abstol : 1e-100;
+  typedef std::chrono::steady_clock clk;
+  auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
   std::vector<double> uaug((size_t)(s + 1) * (s + 1)), alpha(std::max(s, 1));
   if (alg == MSP_ALG_SM) RC(op_update_rhs(e)); // …multisplitting.c:164
   while (!done && res->outer_its < max_outer) {
     if (alg == MSP_ALG_SM) {
       int its = 0, reason = 0;
+      auto t0 = clk::now();
       RC(op_inner_solve(e, &in, true, &its, &reason, nullptr));
+      auto t1 = clk::now();
+      res->stage_inner_s += secs(t0, t1);
       res->inner_its_total += its;
       RC(exchange_sync(e));
       RC(op_update_rhs(e));
@@ -839,17 +936,47 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
       if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = norm;
       if (norm <= thr_global) done = true;
       res->outer_its++;
+      res->stage_outer_s += secs(t1, clk::now());
       continue;
     }
+    auto t_outer0 = clk::now();
+    double inner_this = 0.0;
     for (int t = 0; t < s; t++) {
       RC(op_update_rhs(e));
       int its = 0, reason = 0;
+      auto t0 = clk::now();
       RC(op_inner_solve(e, &in, true, &its, &reason, nullptr));
+      inner_this += secs(t0, clk::now());
       res->inner_its_total += its;
       RC(exchange_sync(e));
       RC(op_push_iterate(e, t));
     }
-    if (alg == MSP_ALG_SMSM_GLOBAL) {
+    if (lsqr) {
+      // the reference's minimiser, literally: LSQR on R = A S with the raw basis (utils.c:1061-1103)
+      int lits = 0;
+      double norm = 0.0;
+      RC(op_spmm(e, alg, s, false));
+      if (alg == MSP_ALG_SMSM_LOCAL) RC(op_update_rhs(e));
+      double ln = 0.0;
+      if (alg == MSP_ALG_SMSM_SEMI_LOCAL) { RC(op_resid_sumsq(e, false, 1)); RC(read_scalars(e, 1, 1)); ln = std::sqrt(e->hsc[1]); }
+      RC(op_lsqr(e, alg, s, alg == MSP_ALG_SMSM_GLOBAL, lsqr_max_it, lsqr_rtol, lsqr_abstol, alpha.data(), &norm, &lits));
+      res->outer_solver_its += lits;
+      RC(op_apply_alpha(e, alg, s, alpha.data()));
+      if (alg == MSP_ALG_SMSM_GLOBAL) {
+        res->last_norm = norm; // KSPGetResidualNorm(outer_ksp) = phibar (…-global.c:343)
+        if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = norm;
+        if (norm <= thr_global) done = true;
+      } else {
+        if (alg == MSP_ALG_SMSM_LOCAL) { RC(op_resid_sumsq(e, false, 1)); RC(read_scalars(e, 1, 1)); ln = std::sqrt(e->hsc[1]); }
+        if (ln <= thr_local) sticky = 1;
+        e->hsc[2] = sticky; e->hsc[3] = ln * ln;
+        CK(cudaMemcpyAsync(e->dsc + 2, e->hsc + 2, 16, cudaMemcpyHostToDevice, e->st));
+        RC(allreduce_host(e, 2, 2));
+        res->last_norm = ln;
+        if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = ln;
+        if ((int)std::lround(e->hsc[2]) == G) done = true;
+      }
+    } else if (alg == MSP_ALG_SMSM_GLOBAL) {
       RC(op_spmm(e, alg, s));
       RC(op_local_qr(e, alg, s, uaug.data()));
       // TSQR: gather every block's factor (zero-padded allreduce = allgather), identical small solve everywhere
@@ -908,6 +1035,8 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
       MSP_FAIL("algorithm not handled by the synchronous driver");
     }
     res->outer_its++;
+    res->stage_inner_s += inner_this;
+    res->stage_outer_s += secs(t_outer0, clk::now()) - inner_this;
   }
   RC(e->comm->barrier(e->st));
   CK(cudaEventRecord(ev1, e->st));
@@ -1486,6 +1615,7 @@ static int async_publish(msp_engine *e, int iter) {
 static int async_begin(msp_engine *e, const msp_solve_opts *o, msp_result *res, AsyncRun *run) {
   const int G = e->prob.nblocks, s = o->s;
   memset(res, 0, sizeof(*res));
+  if (o->outer_type == 1) MSP_FAIL("the LSQR minimiser is available for the synchronous variants only");
   if (o->alg != MSP_ALG_AM && (s < 1 || s > e->smax)) MSP_FAIL("s exceeds the engine's basis storage");
   for (int side = 0; side < 2; side++)
     if (e->has_nb[side] && !e->peer[side].base) MSP_FAIL("neighbour window not connected");

@@ -728,6 +728,10 @@ __global__ void k_scale_by_inv(long long n, const double *norm, double *w) {
   const double inv = nv > 0.0 ? 1.0 / nv : 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) w[i] *= inv;
 }
+// w *= a  (VecScale)
+__global__ void k_scale(long long n, double a, double *w) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) w[i] *= a;
+}
 // x[r] = sum_t alpha[t] S[t][r]   (MatMult(S, alpha, x) utils.c:1075), plus the stored boundaries
 __global__ void k_lincomb(int nb, int s, long long lds, const double *__restrict__ S, const double *__restrict__ alpha, double *__restrict__ x) {
   __shared__ double al[64];

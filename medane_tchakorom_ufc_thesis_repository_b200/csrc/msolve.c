@@ -9,7 +9,8 @@
  * like the PETSc options database does, and prints the log lines the reference's log scrapers rely on
  * (utils.c:668-729).  All numerics happen behind the C-ABI of libmsplit.so (include/msplit.h).
  *
- * Extensions: -alg <iSolve name | reference binary name>, -p <depth> (3-D, poisson3DMatrix), -nblocks G
+ * Extensions: -minimizer tsqr|lsqr (default tsqr = exact least squares; lsqr = the reference's PETSc LSQR, driven by
+ * -outer{K}_ksp_max_it / -outer{K}_ksp_rtol / -outer{K}_ksp_atol), -alg <iSolve name | reference binary name>, -p <depth> (3-D, poisson3DMatrix), -nblocks G
  * (default: the reference's np/npb = 2; 1 for GMRES), -devices 0,1,... (one entry per block, default: block K on
  * GPU K mod #GPUs), -max_outer N, -period a,b,... (deterministic asynchronous schedule, tests only).
  */
@@ -169,8 +170,24 @@ int main(int argc, char **argv) {
       else if (memcmp(&o, &first, sizeof o)) { fprintf(stderr, "msolve: -inner%d_* differs from -inner1_*: per-block inner options must agree\n", k); return 2; }
     }
     inner = first;
-    /* outer{K}_ksp_* select the reference's LSQR/CG settings; the device minimiser is an exact least-squares solve
-     * (TSQR), so they are accepted and ignored — exactly what "-options_left" would report as unused */
+    /* outer{K}_ksp_* select the reference's LSQR settings; they drive the device LSQR when -minimizer lsqr is given and
+     * are otherwise unused (the default minimiser is an exact least-squares solve, TSQR) */
+  }
+  int outer_type = 0, outer_max_it = 100;
+  double outer_rtol = 1e-15, outer_atol = 1e-100;
+  {
+    const char *mz = opt_find(&db, "-minimizer", NULL);
+    if (mz && *mz) {
+      if (!strcasecmp(mz, "lsqr")) outer_type = 1;
+      else if (strcasecmp(mz, "tsqr") && strcasecmp(mz, "qr")) { fprintf(stderr, "msolve: -minimizer %s unknown (tsqr | lsqr)\n", mz); return 2; }
+    }
+    const char *pre[] = {"outer_", "outer1_"};
+    for (int i = 0; i < 2; i++) {
+      char key[64];
+      snprintf(key, sizeof key, "-%sksp_max_it", pre[i]); opt_int(&db, key, &outer_max_it);
+      snprintf(key, sizeof key, "-%sksp_rtol", pre[i]); opt_real(&db, key, &outer_rtol);
+      snprintf(key, sizeof key, "-%sksp_atol", pre[i]); opt_real(&db, key, &outer_atol);
+    }
   }
 
   int devices[MSP_MAX_BLOCKS], periods[MSP_MAX_BLOCKS];
@@ -217,6 +234,7 @@ int main(int argc, char **argv) {
   msp_solve_opts so;
   memset(&so, 0, sizeof so);
   so.alg = alg; so.s = uses_s ? s : 0; so.rtol = rtol; so.inner = inner; so.max_outer = max_outer; so.record_history = 1;
+  so.outer_type = outer_type; so.outer_max_it = outer_max_it; so.outer_rtol = outer_rtol; so.outer_abstol = outer_atol;
   for (int k = 0; k < nblocks; k++) so.period[k] = periods[k];
   msp_result *res = (msp_result *)calloc((size_t)nblocks, sizeof(msp_result));
   CHECK(msp_group_solve(g, &so, res));
@@ -233,6 +251,12 @@ int main(int argc, char **argv) {
   }
   printf("Final residual norm 2 = %e \n", res[0].final_residual); /* utils.c:699 */
   printf("Erreur : %e \n", res[0].error);                        /* …multisplitting.c:229 */
+  if (opt_flag(&db, "-log_view")) {
+    /* the reference's PetscLogStage split (…-global.c:81-89), host seconds of block 0 */
+    printf("Stage I_Solver (inner GMRES solves): %f s\n", res[0].stage_inner_s);
+    printf("Stage O_Solver (exchange, A*S, minimisation, convergence test): %f s\n", res[0].stage_outer_s);
+    if (res[0].outer_solver_its) printf("Outer solver (LSQR) iterations: %lld\n", (long long)res[0].outer_solver_its);
+  }
   long long launches = 0;
   for (int k = 0; k < nblocks; k++) launches += (long long)res[k].kernel_launches;
   printf("[msolve] alg=%s blocks=%d gpus=%d rel_residual=%e kernel_launches=%lld\n", algname, nblocks, ngpu,

@@ -231,8 +231,9 @@ class Engine:
     def comm_connect_block(self, block: int, handle: bytes):
         check(_lib.lib().msp_comm_connect_block(self.h, block, handle))
 
-    def solve(self, alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_outer=0, record_history=True, profile=False):
-        o = make_solve_opts(alg, s, rtol, inner, max_outer, record_history, profile=profile)
+    def solve(self, alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_outer=0, record_history=True, profile=False,
+              **outer):
+        o = make_solve_opts(alg, s, rtol, inner, max_outer, record_history, profile=profile, **outer)
         res = Result()
         check(_lib.lib().msp_solve(self.h, C.byref(o), C.byref(res)))
         return res.as_dict()
@@ -254,7 +255,8 @@ def comm_unique_id() -> bytes:
 
 
 def make_solve_opts(alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_outer=0, record_history=True,
-                    periods: Optional[Sequence[int]] = None, profile=False) -> SolveOpts:
+                    periods: Optional[Sequence[int]] = None, profile=False, outer_type="tsqr", outer_max_it=100,
+                    outer_rtol=1e-15, outer_abstol=1e-100) -> SolveOpts:
     o = SolveOpts()
     o.alg = ALG[alg] if isinstance(alg, str) else int(alg)
     o.s = s
@@ -263,6 +265,8 @@ def make_solve_opts(alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_ou
     o.max_outer = max_outer
     o.record_history = int(record_history)
     o.profile = int(profile)
+    o.outer_type = 1 if outer_type == "lsqr" else 0
+    o.outer_max_it, o.outer_rtol, o.outer_abstol = outer_max_it, outer_rtol, outer_abstol
     for i in range(_lib.MAX_BLOCKS):
         o.period[i] = periods[i] if periods and i < len(periods) else 0
     return o
@@ -296,8 +300,8 @@ class Group:
             pass
 
     def solve(self, alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_outer=0, record_history=True, periods=None,
-              profile=False):
-        o = make_solve_opts(alg, s, rtol, inner, max_outer, record_history, periods, profile)
+              profile=False, **outer):
+        o = make_solve_opts(alg, s, rtol, inner, max_outer, record_history, periods, profile, **outer)
         res = (Result * self.nblocks)()
         check(_lib.lib().msp_group_solve(self.h, C.byref(o), res))
         return [r.as_dict() for r in res]

@@ -328,6 +328,54 @@ def test_async_free_running_reaches_residual(S, alg, s, G):
     grp.close()
 
 
+def test_time_to_rtol_1024_one_block(S):
+    """The metric as BASELINE.json names it (SMSM time-to-rtol 1e-6), on a grid where it is reachable: 1024x1024, one
+    block; outer-iteration count against the oracle run recorded in tests/golden/smsm_global_1024_to_rtol.json."""
+    with open(os.path.join(GOLD, "smsm_global_1024_to_rtol.json")) as f:
+        gold = json.load(f)
+    e = S.Engine(1024, 1024, s=5, max_restart=30)
+    res = e.solve("SMSM_GLOBAL", s=5, rtol=1e-6, inner=S.ksp_opts(restart=30, max_it=20, rtol=1e-10, abstol=1e-100), max_outer=5000)
+    assert abs(res["outer_its"] - gold["outer_its"]) <= 1, (res["outer_its"], gold["outer_its"])
+    assert res["final_residual"] <= 1e-6 * res["norm0"] * 1.000001
+    n = min(len(res["hist"]), len(gold["hist"]), 10)
+    assert np.allclose(res["hist"][:n], gold["hist"][:n], rtol=1e-6)
+    assert res["elapsed_s"] < 30.0
+    e.close()
+
+
+@pytest.mark.parametrize("alg,G", [("SMSM_GLOBAL", 2), ("SMSM_SEMI_LOCAL", 2), ("SMSM_LOCAL", 2), ("SMSM_GLOBAL", 1)])
+def test_lsqr_minimiser_matches_oracle_lsqr(S, oracle, alg, G):
+    """-minimizer lsqr: the reference's own outer solver (PETSc LSQR, zero guess, max_it iterations) on the device,
+    against the oracle's LSQR restatement: first outer iterations value for value, then the iteration count."""
+    inner = dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)
+    kw = dict(outer_type="lsqr", outer_max_it=40, outer_rtol=1e-15)
+    grp = S.Group(32, 32, nblocks=G, s=4, max_restart=30)
+    res = grp.solve(alg, s=4, rtol=1e-300, inner=S.ksp_opts(**inner), max_outer=2, **kw)
+    ref = oracle.solve(alg, 32, 32, nblocks=G, s=4, rtol=1e-300, inner=inner, max_outer=2, outer_type="lsqr", outer_max_it=40, outer_rtol=1e-15)
+    x = grp.solution()
+    assert np.linalg.norm(x - ref["x"]) <= 1e-7 * np.linalg.norm(ref["x"])
+    assert res[0]["outer_solver_its"] == 80  # inconsistent system + rtol 1e-15: LSQR always runs max_it (SURVEY A.7)
+    grp.close()
+    grp = S.Group(32, 32, nblocks=G, s=4, max_restart=30)
+    res = grp.solve(alg, s=4, rtol=1e-5, inner=S.ksp_opts(**inner), max_outer=2000, **kw)
+    ref = oracle.solve(alg, 32, 32, nblocks=G, s=4, rtol=1e-5, inner=inner, max_outer=2000, outer_type="lsqr", outer_max_it=40, outer_rtol=1e-15)
+    assert abs(res[0]["outer_its"] - ref["outer_its"]) <= 1, (res[0]["outer_its"], ref["outer_its"])
+    grp.close()
+
+
+def test_modified_gram_schmidt_option(S, oracle):
+    """-ksp_gmres_modifiedgramschmidt and the two CGS refinement types give the oracle's iteration counts."""
+    N = 40
+    rp, ci, va = oracle.poisson2d_complete(N, N)
+    b = oracle.spmv(rp, ci, va, np.ones(N * N))
+    e = S.Engine(N, N, max_restart=20)
+    r = e.gmres_solve(S.ksp_opts(restart=20, max_it=400, rtol=1e-8, abstol=1e-100, initial_rtol=1, mgs=1))
+    x, its, reason, rnorm = oracle.gmres(rp, ci, va, b, restart=20, max_it=400, rtol=1e-8, abstol=1e-100, initial_rtol=1, mgs=1)
+    assert abs(r["gmres_its"] - its) <= 1 and r["gmres_reason"] == reason
+    assert np.linalg.norm(e.x - x) <= 1e-6 * np.linalg.norm(x)
+    e.close()
+
+
 def test_one_line_blocks(S, oracle):
     """Edge case: every block is a single grid line, so each row couples to both neighbours."""
     inner = dict(restart=30, max_it=4, rtol=1e-10, abstol=1e-100)
