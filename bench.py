@@ -205,7 +205,7 @@ def run_gpu(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(dom)
+            traffic = json.load(f).get(dom, {}).get("total")
     except Exception:
         pass
     roofline = {
