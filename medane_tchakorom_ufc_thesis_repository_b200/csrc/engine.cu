@@ -191,6 +191,7 @@ struct msp_engine {
   GmresCtl *ctl = nullptr;
   ReduceWs ws{};
   double *dsc = nullptr; // device scalars [256]
+  double *dfac = nullptr; // device staging of the stacked TSQR factors [G x (smax+1)^2]
   double *hsc = nullptr; // pinned host scalars [256]
   Window win;            // own receive window
   Window peer[2];        // neighbours' windows (peer / IPC mapped); base null if no neighbour
@@ -308,13 +309,34 @@ static int set_device(int device) {
 // ------------------------------------------------------------------------------------------------
 // kernel launch helpers (every launch is counted: bench.py reports gpu_launches)
 // ------------------------------------------------------------------------------------------------
+// resident blocks per SM of a kernel (cached): grids of the grid-stride kernels are SMs x this, i.e. exactly one full
+// wave, whatever register count ptxas chose (the 7-point SpMV needs 40 registers: 6 blocks per SM, not 8)
+template <typename K>
+static int resident_blocks_per_sm(K kernel) {
+  static std::mutex mu;
+  static std::map<const void *, int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find((const void *)kernel);
+  if (it != cache.end()) return it->second;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, MSPK_THREADS, 0) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 4; }
+  cache[(const void *)kernel] = nb;
+  return nb;
+}
 template <int MODE, bool RESID, bool SCALE, bool NORM>
 static void launch_spmv_w(msp_engine *e, const SpmvArgs &a, int ws_slot, GmresCtl *ctl_rw) {
-  const int g = grid_for(((long long)a.nb + 1) / 2, 8);
+  const long long items = ((long long)a.nb + 1) / 2;
   e->prof_begin(0, 12.0 * (double)e->nnz + 4.0 * (e->nb + 1) + 16.0 * e->nb + (RESID ? 8.0 * e->nb : 0.0));
-  if (a.W == 5) k_spmv_ell<5, MODE, RESID, SCALE, NORM><<<g, MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
-  else if (a.W == 7) k_spmv_ell<7, MODE, RESID, SCALE, NORM><<<g, MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
-  else k_spmv_ell<0, MODE, RESID, SCALE, NORM><<<g, MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
+  if (a.W == 5) {
+    auto k = k_spmv_ell<5, MODE, RESID, SCALE, NORM>;
+    k<<<grid_for(items, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
+  } else if (a.W == 7) {
+    auto k = k_spmv_ell<7, MODE, RESID, SCALE, NORM>;
+    k<<<grid_for(items, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
+  } else {
+    auto k = k_spmv_ell<0, MODE, RESID, SCALE, NORM>;
+    k<<<grid_for(items, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
+  }
   e->prof_end();
   e->launches++;
 }
@@ -373,7 +395,7 @@ static int engine_free(msp_engine *e) {
   for (int J = 0; J < MSP_MAX_BLOCKS; J++)
     if (e->peer_any[J].base && e->peer_any_ipc[J]) cudaIpcCloseMemHandle(e->peer_any[J].base);
   void *ptrs[] = {e->rp, e->ci, e->va, e->ecol, e->eval, e->brow, e->b, e->rhs, e->x, e->halo[0], e->halo[1], e->V, e->Wb[0],
-                  e->Wb[1], e->S, e->Slo, e->Shi, e->R, e->ctl, e->ws.partial, e->ws.counter, e->dsc, e->win.base, e->cd, e->aint, e->dec};
+                  e->Wb[1], e->S, e->Slo, e->Shi, e->R, e->ctl, e->ws.partial, e->ws.counter, e->dsc, e->dfac, e->win.base, e->cd, e->aint, e->dec};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (e->hsc) cudaFreeHost(e->hsc);
   if (e->own_comm && e->comm) delete e->comm;
@@ -457,6 +479,7 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   }
   dalloc(&e->ws.partial, sizeof(double) * (size_t)MSPK_MAX_PART * 8 * 24);
   dalloc(&e->dsc, sizeof(double) * 256);
+  dalloc(&e->dfac, sizeof(double) * (size_t)p->nblocks * (e->smax + 1) * (e->smax + 1) + 64);
   e->win.H = e->H; e->win.G = p->nblocks; e->win.fslot = Window::fslot_for(e->smax);
   e->win.bytes = Window::size_for(e->H, p->nblocks, e->smax);
   dalloc(&e->win.base, e->win.bytes);
@@ -983,14 +1006,11 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
       const int nn = (s + 1) * (s + 1);
       std::vector<double> all((size_t)G * nn, 0.0);
       if (G > 1) {
-        double *dall = nullptr;
-        CK(cudaMalloc(&dall, sizeof(double) * (size_t)G * nn));
         memcpy(all.data() + (size_t)e->prob.block * nn, uaug.data(), sizeof(double) * nn);
-        CK(cudaMemcpyAsync(dall, all.data(), sizeof(double) * (size_t)G * nn, cudaMemcpyHostToDevice, e->st));
-        RC(e->comm->allreduce_sum(dall, G * nn, e->st));
-        CK(cudaMemcpyAsync(all.data(), dall, sizeof(double) * (size_t)G * nn, cudaMemcpyDeviceToHost, e->st));
+        CK(cudaMemcpyAsync(e->dfac, all.data(), sizeof(double) * (size_t)G * nn, cudaMemcpyHostToDevice, e->st));
+        RC(e->comm->allreduce_sum(e->dfac, G * nn, e->st));
+        CK(cudaMemcpyAsync(all.data(), e->dfac, sizeof(double) * (size_t)G * nn, cudaMemcpyDeviceToHost, e->st));
         CK(cudaStreamSynchronize(e->st));
-        CK(cudaFree(dall));
       } else {
         all = uaug;
       }
@@ -1359,17 +1379,17 @@ int msp_tsqr_combine(int s, int nfac, const double *u_aug_all, double *alpha, do
 int msp_op_spmv(msp_engine *e, int which, const double *x, const double *halo_lo, const double *halo_hi, double *y) {
   if (!e || !x || !y) MSP_FAIL("null argument");
   cudaSetDevice(e->device);
-  double *dlo = nullptr, *dhi = nullptr;
+  // staging: the first two boundary buffers of the own receive window (idle outside a solve)
+  double *dlo = halo_lo ? e->win.halo(0, 0) : nullptr, *dhi = halo_hi ? e->win.halo(1, 0) : nullptr;
   CK(cudaMemcpyAsync(e->Wb[0], x, sizeof(double) * e->nb, cudaMemcpyHostToDevice, e->st));
-  if (halo_lo) { CK(cudaMalloc(&dlo, sizeof(double) * e->H)); CK(cudaMemcpyAsync(dlo, halo_lo, sizeof(double) * e->H, cudaMemcpyHostToDevice, e->st)); }
-  if (halo_hi) { CK(cudaMalloc(&dhi, sizeof(double) * e->H)); CK(cudaMemcpyAsync(dhi, halo_hi, sizeof(double) * e->H, cudaMemcpyHostToDevice, e->st)); }
+  if (halo_lo) CK(cudaMemcpyAsync(dlo, halo_lo, sizeof(double) * e->H, cudaMemcpyHostToDevice, e->st));
+  if (halo_hi) CK(cudaMemcpyAsync(dhi, halo_hi, sizeof(double) * e->H, cudaMemcpyHostToDevice, e->st));
   SpmvArgs a = spmv_args(e, e->Wb[0], e->Wb[1]);
   if (which == MSP_MAT_DIAG) launch_spmv_w<0, false, false, false>(e, a, 0, nullptr);
   else if (which == MSP_MAT_STRIP) { a.lo = dlo; a.hi = dhi; launch_spmv_w<1, false, false, false>(e, a, 0, nullptr); }
   else MSP_FAIL("which must be STRIP or DIAG");
   CK(cudaMemcpyAsync(y, e->Wb[1], sizeof(double) * e->nb, cudaMemcpyDeviceToHost, e->st));
   CK(cudaStreamSynchronize(e->st));
-  cudaFree(dlo); cudaFree(dhi);
   return 0;
 }
 int msp_op_mdot(msp_engine *e, int nv, const double *V, const double *w, double *h) {

@@ -156,7 +156,8 @@ def test_update_rhs_and_residuals(S, oracle):
 
 # ------------------------------------------------------------------ GMRES (inner_solver / gmres_solution)
 @pytest.mark.parametrize("N,restart,max_it,rtol,refine", [(32, 30, 1000, 1e-8, 0), (48, 10, 200, 1e-6, 0), (32, 30, 7, 1e-30, 0),
-                                                            (40, 20, 500, 1e-9, 2), (40, 20, 500, 1e-9, 1)])
+                                                            (40, 20, 500, 1e-9, 2), (40, 20, 500, 1e-9, 1),
+                                                            (96, 50, 100000, 1e-4, 0)])  # config 2's options on a small grid
 def test_standalone_gmres_matches_oracle(S, oracle, N, restart, max_it, rtol, refine):
     e = S.Engine(N, N, max_restart=restart)
     o = S.ksp_opts(restart=restart, max_it=max_it, rtol=rtol, abstol=1e-100, initial_rtol=1, cgs_refine=refine)
