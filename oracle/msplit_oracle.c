@@ -760,6 +760,14 @@ static int blk_setup(const orc_config *c, int K, blk *B, int64_t ntot) {
   for (int64_t i = 0; i < ntot; i++) ones[i] = 1.0;
   orc_spmv(B->nb, B->rp, B->ci, B->va, ones, B->b);
   free(ones);
+  /* sensitivity experiments only: ORC_PERTURB_B=eps multiplies b_i by (1 + eps sin(i)) */
+  {
+    const char *pe = getenv("ORC_PERTURB_B");
+    if (pe && *pe) {
+      const double eps = atof(pe);
+      for (int i = 0; i < B->nb; i++) B->b[i] *= (1.0 + eps * sin((double)(B->off + i)));
+    }
+  }
   return 0;
 }
 
