@@ -171,7 +171,8 @@ int msp_op_spmv(msp_engine *e, int which, const double *x, const double *halo_lo
 int msp_op_mdot(msp_engine *e, int nv, const double *V /* nv x nb */, const double *w, double *h);
 int msp_op_maxpy(msp_engine *e, int nv, const double *V, const double *coef, double *w /* in/out */, double *norm);
 /* device micro-benchmark of the hot kernels on this engine's resident data: returns average ms per launch.
- * op: 0 spmv(ELL), 1 mdot(nv), 2 maxpy+norm(nv), 3 spmm(s), 4 copy (STREAM), 5 fused scale+spmv */
+ * op: 0 spmv(ELL), 1 mdot(nv), 2 maxpy+norm(nv), 3 spmm(s), 4 copy (STREAM), 5 spmv with the input scaled on the fly,
+ *     6 Gram contraction of nv columns */
 int msp_bench_kernel(msp_engine *e, int op, int nv, int iters, int flush_l2, double *ms_avg);
 
 /* standalone GMRES (gmres_solution.c:50-85): b = A 1, x0 = 0, one KSPSolve */

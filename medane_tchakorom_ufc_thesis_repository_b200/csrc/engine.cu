@@ -192,6 +192,8 @@ struct msp_engine {
   ReduceWs ws{};
   double *dsc = nullptr; // device scalars [256]
   double *dfac = nullptr; // device staging of the stacked TSQR factors [G x (smax+1)^2]
+  double *gram_partial = nullptr; // [45 x MSPK_MAX_PART] partials of the Gram kernel
+  bool use_cholqr = true;
   double *hsc = nullptr; // pinned host scalars [256]
   Window win;            // own receive window
   Window peer[2];        // neighbours' windows (peer / IPC mapped); base null if no neighbour
@@ -395,7 +397,7 @@ static int engine_free(msp_engine *e) {
   for (int J = 0; J < MSP_MAX_BLOCKS; J++)
     if (e->peer_any[J].base && e->peer_any_ipc[J]) cudaIpcCloseMemHandle(e->peer_any[J].base);
   void *ptrs[] = {e->rp, e->ci, e->va, e->ecol, e->eval, e->brow, e->b, e->rhs, e->x, e->halo[0], e->halo[1], e->V, e->Wb[0],
-                  e->Wb[1], e->S, e->Slo, e->Shi, e->R, e->ctl, e->ws.partial, e->ws.counter, e->dsc, e->dfac, e->win.base, e->cd, e->aint, e->dec};
+                  e->Wb[1], e->S, e->Slo, e->Shi, e->R, e->ctl, e->ws.partial, e->ws.counter, e->dsc, e->dfac, e->gram_partial, e->win.base, e->cd, e->aint, e->dec};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (e->hsc) cudaFreeHost(e->hsc);
   if (e->own_comm && e->comm) delete e->comm;
@@ -480,6 +482,8 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   dalloc(&e->ws.partial, sizeof(double) * (size_t)MSPK_MAX_PART * 8 * 24);
   dalloc(&e->dsc, sizeof(double) * 256);
   dalloc(&e->dfac, sizeof(double) * (size_t)p->nblocks * (e->smax + 1) * (e->smax + 1) + 64);
+  if (e->smax > 0) dalloc(&e->gram_partial, sizeof(double) * 45 * MSPK_MAX_PART);
+  e->use_cholqr = getenv("MSPLIT_NO_CHOLQR") == nullptr;
   e->win.H = e->H; e->win.G = p->nblocks; e->win.fslot = Window::fslot_for(e->smax);
   e->win.bytes = Window::size_for(e->H, p->nblocks, e->smax);
   dalloc(&e->win.base, e->win.bytes);
@@ -726,15 +730,57 @@ static int op_spmm(msp_engine *e, int kind, int s, bool diff_basis = true) {
   return 0;
 }
 
-// TSQR leaf: classical Gram-Schmidt with reorthogonalisation (CGS2) on [R_K | rhs] using the Arnoldi
-// kernels (K3, K4+K5).  Q overwrites R; the (s+1)x(s+1) upper factor goes to the host (column-major).
-static int op_local_qr(msp_engine *e, int kind, int s, double *u_aug /* host (s+1)^2 */) {
-  const int nc = s + 1;
-  const double *rhs_src = kind_is_local(kind) ? e->rhs : e->b;
-  k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, rhs_src, e->R + (long long)s * e->ld);
+// upper Cholesky factor of a symmetric NC x NC matrix given by its upper triangle (column-major); false on breakdown
+static bool chol_upper(int nc, const double *G, double *U) {
+  std::fill(U, U + nc * nc, 0.0);
+  double dmax = 0.0;
+  for (int j = 0; j < nc; j++) dmax = std::max(dmax, G[j * nc + j]);
+  for (int j = 0; j < nc; j++) {
+    for (int i = 0; i <= j; i++) {
+      double t = G[j * nc + i];
+      for (int k = 0; k < i; k++) t -= U[i * nc + k] * U[j * nc + k];
+      if (i < j) U[j * nc + i] = t / U[i * nc + i];
+      else {
+        if (!(t > 1e-13 * dmax)) return false; // not safely positive definite at working precision
+        U[j * nc + j] = std::sqrt(t);
+      }
+    }
+  }
+  return true;
+}
+
+template <int NC>
+static void launch_gram_nc(msp_engine *e, const double *C, double *out_dev) {
+  auto k = k_gram<NC>;
+  k<<<grid_for((long long)e->nb / 2, std::min(resident_blocks_per_sm(k), 4)), MSPK_THREADS, 0, e->st>>>(e->nb, e->ld, C, e->gram_partial, e->ws.counter + 40, out_dev);
   e->launches++;
-  // device scratch: dsc[64..64+nc) coefficients pass 1, dsc[128..) pass 2, dsc[200] norm; U assembled in dsc? -> use hsc after each column
-  std::vector<double> U((size_t)nc * nc, 0.0);
+}
+template <int NC>
+static void launch_trsolve_nc(msp_engine *e, double *C, const double *U_dev) {
+  auto k = k_right_trsolve<NC>;
+  k<<<grid_for(e->nb, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(e->nb, e->ld, C, U_dev);
+  e->launches++;
+}
+static void launch_gram(msp_engine *e, int nc, const double *C, double *out_dev) {
+  switch (nc) {
+    case 2: launch_gram_nc<2>(e, C, out_dev); break; case 3: launch_gram_nc<3>(e, C, out_dev); break;
+    case 4: launch_gram_nc<4>(e, C, out_dev); break; case 5: launch_gram_nc<5>(e, C, out_dev); break;
+    case 6: launch_gram_nc<6>(e, C, out_dev); break; case 7: launch_gram_nc<7>(e, C, out_dev); break;
+    case 8: launch_gram_nc<8>(e, C, out_dev); break; default: launch_gram_nc<9>(e, C, out_dev); break;
+  }
+}
+static void launch_trsolve(msp_engine *e, int nc, double *C, const double *U_dev) {
+  switch (nc) {
+    case 2: launch_trsolve_nc<2>(e, C, U_dev); break; case 3: launch_trsolve_nc<3>(e, C, U_dev); break;
+    case 4: launch_trsolve_nc<4>(e, C, U_dev); break; case 5: launch_trsolve_nc<5>(e, C, U_dev); break;
+    case 6: launch_trsolve_nc<6>(e, C, U_dev); break; case 7: launch_trsolve_nc<7>(e, C, U_dev); break;
+    case 8: launch_trsolve_nc<8>(e, C, U_dev); break; default: launch_trsolve_nc<9>(e, C, U_dev); break;
+  }
+}
+
+// CGS2 leaf (classical Gram-Schmidt with reorthogonalisation, the Arnoldi kernels K3, K4+K5) on the nc columns at e->R
+static int local_qr_cgs2(msp_engine *e, int nc, std::vector<double> &U) {
+  U.assign((size_t)nc * nc, 0.0);
   for (int c = 0; c < nc; c++) {
     double *q = e->R + (long long)c * e->ld;
     if (c > 0) {
@@ -752,7 +798,59 @@ static int op_local_qr(msp_engine *e, int kind, int s, double *u_aug /* host (s+
     for (int j = 0; j < c; j++) U[(size_t)c * nc + j] = -(e->hsc[64 + j] + e->hsc[128 + j]);
     U[(size_t)c * nc + c] = e->hsc[200];
   }
-  memcpy(u_aug, U.data(), sizeof(double) * (size_t)nc * nc);
+  return 0;
+}
+
+// TSQR leaf: the (s+1)x(s+1) upper factor of [R_K | rhs] (column-major, to the host).
+//  * s <= 8: CholeskyQR2 — Gram contraction (K9, one pass), Cholesky on the host, C := C U1^{-1} (one pass), Gram again,
+//    U = U2 U1: 24 n (s+1) bytes instead of the ~16 n (s+1)(s+3) of Gram-Schmidt, and as accurate as Householder QR
+//    while cond([R|rhs]) < ~1e7; a Cholesky breakdown falls back to
+//  * CGS2 with the Arnoldi kernels (any s, any conditioning), continuing from whatever basis is in place.
+static int op_local_qr(msp_engine *e, int kind, int s, double *u_aug /* host (s+1)^2 */) {
+  const int nc = s + 1;
+  const double *rhs_src = kind_is_local(kind) ? e->rhs : e->b;
+  k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, rhs_src, e->R + (long long)s * e->ld);
+  e->launches++;
+  std::vector<double> U, U1, U2, G((size_t)nc * nc, 0.0);
+  bool have_u1 = false;
+  if (e->use_cholqr && nc >= 2 && nc <= 9) {
+    U1.assign((size_t)nc * nc, 0.0); U2.assign((size_t)nc * nc, 0.0);
+    double *Gdev = e->dfac; // idle between TSQR gathers; (smax+1)^2 doubles fit
+    launch_gram(e, nc, e->R, Gdev);
+    CK(cudaMemcpyAsync(G.data(), Gdev, sizeof(double) * nc * nc, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    if (chol_upper(nc, G.data(), U1.data())) {
+      CK(cudaMemcpyAsync(Gdev, U1.data(), sizeof(double) * nc * nc, cudaMemcpyHostToDevice, e->st));
+      launch_trsolve(e, nc, e->R, Gdev);
+      have_u1 = true;
+      launch_gram(e, nc, e->R, Gdev);
+      CK(cudaMemcpyAsync(G.data(), Gdev, sizeof(double) * nc * nc, cudaMemcpyDeviceToHost, e->st));
+      CK(cudaStreamSynchronize(e->st));
+      if (chol_upper(nc, G.data(), U2.data())) {
+        // U = U2 U1
+        for (int j = 0; j < nc; j++)
+          for (int i = 0; i <= j; i++) {
+            double t = 0.0;
+            for (int k = i; k <= j; k++) t += U2[(size_t)k * nc + i] * U1[(size_t)j * nc + k];
+            u_aug[(size_t)j * nc + i] = t;
+          }
+        for (int j = 0; j < nc; j++) for (int i = j + 1; i < nc; i++) u_aug[(size_t)j * nc + i] = 0.0;
+        return 0;
+      }
+    }
+  }
+  RC(local_qr_cgs2(e, nc, U));
+  if (have_u1) {
+    // the columns in place were C U1^{-1}: overall factor = U_cgs2 U1
+    for (int j = 0; j < nc; j++)
+      for (int i = 0; i < nc; i++) {
+        double t = 0.0;
+        for (int k = i; k <= j; k++) t += U[(size_t)k * nc + i] * U1[(size_t)j * nc + k];
+        u_aug[(size_t)j * nc + i] = (i <= j) ? t : 0.0;
+      }
+  } else {
+    memcpy(u_aug, U.data(), sizeof(double) * (size_t)nc * nc);
+  }
   return 0;
 }
 
@@ -1420,6 +1518,7 @@ int msp_bench_kernel(msp_engine *e, int op, int nv, int iters, int flush_l2, dou
   cudaSetDevice(e->device);
   if ((op == 1 || op == 2) && (nv < 1 || nv > e->nvec)) MSP_FAIL("nv out of range");
   if (op == 3 && (nv < 1 || nv > e->smax)) MSP_FAIL("s out of range");
+  if (op == 6 && (nv < 2 || nv > 9 || nv > e->smax + 1)) MSP_FAIL("gram: 2 <= columns <= min(9, s+1)");
   double *flush = nullptr;
   const size_t flush_bytes = (size_t)256 << 20;
   if (flush_l2) CK(cudaMalloc(&flush, flush_bytes));
@@ -1440,6 +1539,7 @@ int msp_bench_kernel(msp_engine *e, int op, int nv, int iters, int flush_l2, dou
       case 3: RC(op_spmm(e, MSP_ALG_SMSM_GLOBAL, nv)); break;
       case 4: k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, e->Wb[0], e->Wb[1]); break;
       case 5: { SpmvArgs a = spmv_args(e, e->Wb[0], e->Wb[1]); launch_spmv_w<0, false, true, false>(e, a, 0, nullptr); break; }
+      case 6: launch_gram(e, nv, e->R, e->dfac); break;
       default: MSP_FAIL("unknown op");
     }
     CK(cudaEventRecord(e1, e->st));

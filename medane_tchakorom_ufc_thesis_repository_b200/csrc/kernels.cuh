@@ -743,6 +743,85 @@ __global__ void k_lincomb(int nb, int s, long long lds, const double *__restrict
     x[r] = t;
   }
 }
+// ------------------------------------------------------------------------------------------------
+// K9  Gram contraction G = C^T C of the tall-skinny block C = [R_K | rhs] (NC = s+1 <= 9 columns): ONE pass over C
+// (8 n NC bytes) for all NC(NC+1)/2 entries, accumulated in registers, last block reduces in fixed order.
+// Intensity = (NC+1)/8 flop/B <= 1.25: far left of the fp64 ridge, so the kernel is HBM-bound on CUDA cores and
+// fp64 tensor-core MMA (DMMA) has nothing to win here.
+// ------------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(MSPK_THREADS) k_gram(int nb, long long ld, const double *__restrict__ C, double *partial, unsigned int *counter,
+                                                       double *out /* NC*NC, column-major, upper triangle filled */) {
+  constexpr int NT = NC * (NC + 1) / 2;
+  double acc[NT];
+#pragma unroll
+  for (int t = 0; t < NT; t++) acc[t] = 0.0;
+  const long long npairs = nb >> 1;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npairs; p += (long long)gridDim.x * blockDim.x) {
+    double2 v[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) v[c] = ld_stream2(C + c * ld + 2 * p);
+    int t = 0;
+#pragma unroll
+    for (int j = 0; j < NC; j++)
+#pragma unroll
+      for (int i = 0; i <= j; i++, t++) acc[t] = fma(v[i].y, v[j].y, fma(v[i].x, v[j].x, acc[t]));
+  }
+  if ((nb & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int j = 0; j < NC; j++)
+#pragma unroll
+      for (int i = 0; i <= j; i++, t++) acc[t] = fma(C[i * ld + nb - 1], C[j * ld + nb - 1], acc[t]);
+  }
+  __shared__ double sm[32];
+  __shared__ bool last;
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    double bs = block_sum(acc[t], sm);
+    if (threadIdx.x == 0) partial[(long long)t * MSPK_MAX_PART + blockIdx.x] = bs;
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned q = atomicAdd(counter, 1u);
+    last = (q == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    int t = 0;
+    for (int j = 0; j < NC; j++)
+      for (int i = 0; i <= j; i++, t++) {
+        double v = 0.0;
+        for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) v += __ldcg(partial + (long long)t * MSPK_MAX_PART + b);
+        double tot = block_sum(v, sm);
+        if (threadIdx.x == 0) out[j * NC + i] = tot;
+      }
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+// C := C U^{-1} for an upper-triangular U (NC x NC, column-major in `U`): one read+write pass, each thread owns rows.
+template <int NC>
+__global__ void __launch_bounds__(MSPK_THREADS) k_right_trsolve(int nb, long long ld, double *__restrict__ C, const double *__restrict__ U) {
+  __shared__ double u[NC * NC];
+  for (int i = threadIdx.x; i < NC * NC; i += blockDim.x) u[i] = U[i];
+  __syncthreads();
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nb; r += (long long)gridDim.x * blockDim.x) {
+    double y[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) y[c] = C[c * ld + r];
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+      double t = y[j];
+#pragma unroll
+      for (int i = 0; i < j; i++) t = fma(-y[i], u[j * NC + i], t);
+      y[j] = t / u[j * NC + j];
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) C[c * ld + r] = y[c];
+  }
+}
+
 // basis change of the minimisation: [x^1 .. x^s] -> [x^1, x^2-x^1, .., x^s-x^(s-1)] in place (same span, much better
 // conditioned least-squares problem).  One pass, each thread owns a row.
 __global__ void k_diff_basis(long long rows, int s, long long lds, double *__restrict__ S) {

@@ -44,6 +44,7 @@ for nv in (1, 4, 8, 16, 30):
     if nv > restart:
         continue
     rec(f"maxpy+norm nv={nv}", e.bench_kernel(2, nv, iters=10), 8 * n * (nv + 2))
+rec("gram [R|b]^T[R|b] 6 columns", e.bench_kernel(6, 6, iters=10), 8 * n * 6)
 rec("spmm s=5", e.bench_kernel(3, 5, iters=10), 12 * nnz + 4 * n + 8 * n * 5 + 8 * n * 5)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump({"N": N, "dim": 3 if dim3 else 2, "rows": rows}, open(f"gpurun_out/kbench_{N}{'_3d' if dim3 else ''}.json", "w"), indent=1)
