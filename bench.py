@@ -216,6 +216,15 @@ def run_gpu(args):
         "frac_of_8TBs_spec": roof[dom]["GBps"] / 8000.0,
     }
 
+    # boundary exchange: barrier + collection of the layers the neighbours stored over NVLink (latency-bound)
+    if world > 1 and prof["other"]["launches"]:
+        n_ex = prof["other"]["launches"]
+        us = D.reduce_max(prof["other"]["ms"]) * 1e3 / n_ex
+        roofline["exchange"] = {"us_per_exchange": us, "bytes_into_this_block": prof["other"]["bytes"] / n_ex,
+                                "nvlink_peer_GBps_measured_ref": 770.0,
+                                "note": "P2P stores are fused into the solution-update kernel; this is the NCCL 1-double barrier plus "
+                                        "the copy of the received layers: latency-bound, not bandwidth-bound"}
+
     # ---- end-to-end through the public C-ABI with HOST buffers: per step H2D of b and x, one outer iteration, D2H of x ----
     b_host = torch.empty(n_local, dtype=torch.float64).pin_memory().numpy()
     x_host = torch.empty(n_local, dtype=torch.float64).pin_memory().numpy()

@@ -997,9 +997,12 @@ static int tsqr_combine(int s, int nfac, const double *uall, double *alpha, doub
 // ------------------------------------------------------------------------------------------------
 static int exchange_sync(msp_engine *e) {
   // the boundary layers were already stored into the neighbours' windows by k_update_x / k_publish_boundary
-  RC(e->comm->barrier(e->st));
-  RC(op_collect_halos(e));
-  return 0;
+  // (class 3 of the profile = barrier + collection of the received layers; bytes = what crossed NVLink into this block)
+  e->prof_begin(3, 8.0 * e->H * ((e->has_nb[0] ? 1 : 0) + (e->has_nb[1] ? 1 : 0)));
+  int rc = e->comm->barrier(e->st);
+  if (!rc) rc = op_collect_halos(e);
+  e->prof_end();
+  return rc;
 }
 
 static int allreduce_host(msp_engine *e, int first, int n) {
