@@ -712,7 +712,7 @@ static int op_spmm(msp_engine *e, int kind, int s, bool diff_basis = true) {
   const bool local = kind_is_local(kind);
   a.Slo = (!local && e->has_nb[0]) ? e->Slo : nullptr;
   a.Shi = (!local && e->has_nb[1]) ? e->Shi : nullptr;
-  const int g = grid_for(((long long)e->nb + 1) / 2, 4);
+  const int g = grid_for(e->nb, 8);
   for (int c0 = 0; c0 < s;) {
     int nc = std::min(8, s - c0);
     // chunk sizes 8,5,4,2,1 cover every s with few passes over the matrix

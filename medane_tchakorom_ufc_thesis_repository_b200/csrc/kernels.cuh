@@ -684,42 +684,31 @@ struct SpmmArgs {
   double *R;
 };
 
-template <int MODE>
-__device__ __forceinline__ void spmm_gather(const SpmmArgs &a, int c, int c0, int t, double v, double &acc) {
-  if ((unsigned)c < (unsigned)a.nb) acc = fma(v, __ldg(a.S + (long long)(c0 + t) * a.lds + c), acc);
-  else if (MODE == 1) {
-    const double *base = (c < 0) ? a.Slo : a.Shi;
-    const int idx = (c < 0) ? c + a.H : c - a.nb;
-    if (base) acc = fma(v, base[(long long)(c0 + t) * a.H + idx], acc);
-  }
-}
-
-// two rows per thread, 128-bit loads of the values and 64-bit loads of the indices (like k_spmv_ell); the matrix is
-// streamed once for NC columns of S
+// one row per thread (a two-rows-per-thread variant with 128-bit matrix loads measured 40 % slower: the 2 x NC x W
+// scattered gathers per thread, not the matrix stream, bound this kernel)
 template <int MODE, int NC>
 __global__ void __launch_bounds__(MSPK_THREADS) k_spmm_ell(SpmmArgs a, int c0) {
-  const long long npairs = ((long long)a.nb + 1) >> 1;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npairs; p += (long long)gridDim.x * blockDim.x) {
-    const long long r = 2 * p;
-    double acc0[NC], acc1[NC];
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < a.nb; r += (long long)gridDim.x * blockDim.x) {
+    double acc[NC];
 #pragma unroll
-    for (int t = 0; t < NC; t++) { acc0[t] = 0.0; acc1[t] = 0.0; }
+    for (int t = 0; t < NC; t++) acc[t] = 0.0;
     for (int k = 0; k < a.W; k++) {
-      const double2 v = ld_stream2(a.eval + k * a.ld + r);
-      const int2 c = ld_stream_i2(a.ecol + k * a.ld + r);
+      const double v = a.eval[k * a.ld + r];
+      const int c = a.ecol[k * a.ld + r];
+      if ((unsigned)c < (unsigned)a.nb) {
 #pragma unroll
-      for (int t = 0; t < NC; t++) {
-        spmm_gather<MODE>(a, c.x, c0, t, v.x, acc0[t]);
-        spmm_gather<MODE>(a, c.y, c0, t, v.y, acc1[t]);
+        for (int t = 0; t < NC; t++) acc[t] = fma(v, __ldg(a.S + (long long)(c0 + t) * a.lds + c), acc[t]);
+      } else if (MODE == 1) {
+        const double *base = (c < 0) ? a.Slo : a.Shi;
+        const int idx = (c < 0) ? c + a.H : c - a.nb;
+        if (base) {
+#pragma unroll
+          for (int t = 0; t < NC; t++) acc[t] = fma(v, base[(long long)(c0 + t) * a.H + idx], acc[t]);
+        }
       }
     }
-    if (r + 1 < a.nb) {
 #pragma unroll
-      for (int t = 0; t < NC; t++) *reinterpret_cast<double2 *>(a.R + (long long)(c0 + t) * a.lds + r) = make_double2(acc0[t], acc1[t]);
-    } else {
-#pragma unroll
-      for (int t = 0; t < NC; t++) a.R[(long long)(c0 + t) * a.lds + r] = acc0[t];
-    }
+    for (int t = 0; t < NC; t++) a.R[(long long)(c0 + t) * a.lds + r] = acc[t];
   }
 }
 
