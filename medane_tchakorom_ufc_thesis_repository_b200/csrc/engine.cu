@@ -247,7 +247,6 @@ struct msp_engine {
   struct CycleGraph { cudaGraphExec_t exec; int launches; };
   std::map<CycleKey, CycleGraph> cycle_graphs;
   bool use_graphs = true;
-  double local_sig = 0; // sticky convergence signal
   // deterministic turn taking for the emulated asynchronous schedule
   struct msp_group *grp = nullptr;
 };
@@ -379,7 +378,7 @@ static void launch_maxpy(msp_engine *e, int nv, const double *V, long long ldv, 
                          int guard_it, int guard_refine, int pass, int ws_slot, const double *inv = nullptr) {
   MaxpyArgs a{};
   a.nb = e->nb; a.nv = nv; a.ld = ldv; a.V = V; a.coef = coef; a.w = w; a.norm_out = norm_out; a.ctl = e->ctl; a.inv = inv;
-  a.guard_it = guard_it; a.guard_refine = guard_refine; a.pass = pass; a.last_pass = 1;
+  a.guard_it = guard_it; a.guard_refine = guard_refine; a.pass = pass;
   e->prof_begin(2, 8.0 * e->nb * (nv + 2));
   k_maxpy_norm<FIN><<<grid_for((long long)e->nb / 4, 8), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot);
   e->prof_end();

@@ -469,7 +469,6 @@ struct MaxpyArgs {
   GmresCtl *ctl;
   int guard_it, guard_refine;
   int pass;            // CGS pass index (0 or 1)
-  int last_pass;       // this pass closes the step unless refinement is requested
 };
 
 template <int FIN>

@@ -1,3 +1,5 @@
+"""Residual history of SMSM-global at 1024x1024 (one block) next to the oracle run recorded in
+tests/golden/smsm_global_1024_to_rtol.json: where the two trajectories decorrelate.  Needs a GPU."""
 import sys, json, os
 sys.path.insert(0, "/root/repo")
 import numpy as np

@@ -1,3 +1,5 @@
+"""relative ||x_gpu - x_oracle|| after 1/2/3 outer iterations for each minimisation variant,
+block count and inner max_it (32x32).  Needs a GPU."""
 import sys
 sys.path.insert(0, "/root/repo")
 import numpy as np
