@@ -406,6 +406,75 @@ def test_one_line_blocks(S, oracle):
     grp.close()
 
 
+@pytest.mark.parametrize("m,n", [(1, 1), (1, 2), (3, 1), (5, 13), (8, 127), (33, 31)])
+def test_ragged_and_tiny_sizes(S, oracle, m, n):
+    """Tiny and odd row counts (scalar tails of the 128-bit kernels, grids of one block)."""
+    rng = np.random.default_rng(m * 131 + n)
+    e = S.Engine(m, n, s=2, max_restart=4, keep_csr=True)
+    nb = e.nb
+    A = oracle.poisson2d(m, n, 0, 1)
+    for a, b in zip(e.divideSubDomainIntoBlockMatrices(S.MAT_STRIP), A):
+        assert np.array_equal(a, b)
+    x = rng.standard_normal(nb)
+    assert np.array_equal(e.spmv(S.MAT_DIAG, x), oracle.spmv(*A, x))
+    nv = min(4, e.nb) if e.nb > 1 else 1
+    V = rng.standard_normal((nv, nb)); w = rng.standard_normal(nb)
+    h = e.mdot(V, w)
+    assert np.allclose(h, V @ w, rtol=1e-13, atol=1e-13)
+    w2, nrm = e.maxpy(V, -h, w)
+    assert np.allclose(w2, w - h @ V, rtol=1e-13, atol=1e-13) and abs(nrm - np.linalg.norm(w2)) <= 1e-13 * (1 + nrm)
+    r = e.gmres_solve(S.ksp_opts(restart=4, max_it=500, rtol=1e-10, abstol=1e-100, initial_rtol=1))
+    b = oracle.spmv(*A, np.ones(nb))
+    xo, its, reason, _ = oracle.gmres(*A, b, restart=4, max_it=500, rtol=1e-10, abstol=1e-100, initial_rtol=1)
+    assert abs(r["gmres_its"] - its) <= 1 and np.linalg.norm(e.x - xo) <= 1e-8 * np.linalg.norm(xo)
+    e.close()
+
+
+@pytest.mark.parametrize("s", [1, 2, 8, 9, 12])
+def test_minimiser_basis_sizes(S, oracle, s):
+    """TSQR leaf for every basis size: CholeskyQR2 (s <= 8) and the Gram-Schmidt path (s > 8) against exact LS."""
+    rng = np.random.default_rng(s)
+    m, n = 20, 12
+    e = S.Engine(m, n, s=s, max_restart=4)
+    Sg = rng.standard_normal((s, m * n))
+    for t in range(s):
+        e.x = Sg[t]
+        e.push_iterate(t)
+    e.spmm_AS("SMSM_GLOBAL")
+    alpha, rn = S.tsqr_combine(s, [e.minimize_local_qr("SMSM_GLOBAL")])
+    A = oracle.poisson2d(m, n, 0, 1)
+    R = np.stack([oracle.spmv(*A, Sg[t]) for t in range(s)], axis=1)
+    b = oracle.spmv(*A, np.ones(m * n))
+    a_ref, rn_ref = oracle.lstsq_qr(R, b)
+    alpha_raw = alpha - np.append(alpha[1:], 0.0)
+    assert np.allclose(alpha_raw, a_ref, rtol=1e-8, atol=1e-10)
+    assert abs(rn - rn_ref) <= 1e-9 * rn_ref
+    e.close()
+
+
+def test_cholqr_breakdown_falls_back(S, oracle):
+    """Numerically dependent iterates (identical columns): the Cholesky leaf breaks down, Gram-Schmidt takes over and the
+    stacked solve drops the dependent direction instead of producing garbage."""
+    m, n, s = 16, 16, 3
+    e = S.Engine(m, n, s=s, max_restart=4)
+    x = np.linspace(0.0, 1.0, m * n)
+    for t in range(s):
+        e.x = x  # three identical iterates
+        e.push_iterate(t)
+    e.spmm_AS("SMSM_GLOBAL")
+    alpha, rn = S.tsqr_combine(s, [e.minimize_local_qr("SMSM_GLOBAL")])
+    assert np.all(np.isfinite(alpha)) and np.isfinite(rn)
+    e.apply_alpha("SMSM_GLOBAL", alpha)
+    A = oracle.poisson2d(m, n, 0, 1)
+    b = oracle.spmv(*A, np.ones(m * n))
+    r_min = np.linalg.norm(b - oracle.spmv(*A, e.x))
+    # best multiple of x in the least-squares sense
+    Ax = oracle.spmv(*A, x)
+    best = np.linalg.norm(b - Ax * (Ax @ b) / (Ax @ Ax))
+    assert abs(r_min - best) <= 1e-8 * best
+    e.close()
+
+
 def test_errors(S):
     with pytest.raises(S.MsplitError):
         S.Engine(10, 10, nblocks=3)  # grid lines not divisible by the block count
