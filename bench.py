@@ -202,15 +202,20 @@ def run_gpu(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     names = {"spmv": "k_spmv_ell (ELL SpMV fused with the deferred VecNormalize)", "mdot": "k_mdot (VecMDot)",
              "maxpy": "k_maxpy_norm (VecMAXPY + VecNorm + Hessenberg/Givens)"}
-    traffic = None
+    # DRAM traffic of the dominant kernel: ncu's dram__bytes_read+write of one captured launch (profiles/ncu_traffic.json)
+    # scaled by (average algorithmic bytes per launch here) / (algorithmic bytes of the captured launch)
+    traffic, traffic_detail = None, None
+    alg_per_launch = prof[dom]["bytes"] / max(1, prof[dom]["launches"])
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(dom, {}).get("total")
+            traffic_detail = json.load(f).get(dom)
+        traffic = traffic_detail["total"] / traffic_detail["algorithmic_bytes_same_launch"] * alg_per_launch
     except Exception:
         pass
     roofline = {
         "bound": "hbm", "kernel": names[dom], "achieved": roof[dom]["GBps"], "peak": peak, "unit": "GB/s",
-        "frac": roof[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
+        "frac": roof[dom]["GBps"] / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_per_launch,
+        "traffic_detail": traffic_detail, "peak_source": peak_src,
         "per_kernel": {c: {"GBps": round(roof[c]["GBps"], 1), "frac": round(roof[c]["GBps"] / peak, 4),
                            "ms_per_outer_iteration": round(roof[c]["ms"], 3), "launches": roof[c]["launches"]} for c in roof},
         "frac_of_8TBs_spec": roof[dom]["GBps"] / 8000.0,
