@@ -85,7 +85,8 @@ typedef struct {
   int profile;          /* bracket every hot-kernel launch with CUDA events and fill the per-class t_, b_ and n_ fields */
   /* minimiser (outer_solver_norm_equation utils.c:1061-1103): 0 = exact least squares by TSQR (default),
    * 1 = PETSc-faithful LSQR on R with zero initial guess and the initial-residual-norm test, as every shipped
-   * command line selects (-outer{K}_ksp_type lsqr -outer{K}_ksp_max_it 40..200 -outer{K}_ksp_rtol 1e-14..1e-50) */
+   * command line selects (-outer{K}_ksp_type lsqr -outer{K}_ksp_max_it 40..200 -outer{K}_ksp_rtol 1e-14..1e-50),
+   * 2 = normal equations on the Gram matrix R'R (the reference's `outer_solver`, utils.c:972-996), s <= 8 */
   int outer_type;
   int outer_max_it;
   double outer_rtol, outer_abstol;

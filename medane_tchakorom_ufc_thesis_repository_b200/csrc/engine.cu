@@ -949,6 +949,52 @@ static int op_lsqr(msp_engine *e, int kind, int s, bool global, int max_it, doub
   return 0;
 }
 
+// Normal-equations minimiser (the reference's `outer_solver`, utils.c:972-996: MatTransposeMatMult(R,R), MatMultTranspose(R,b),
+// KSPSolve on the s x s system): ONE Gram pass over [R_K | rhs] (K9), one allreduce of the (s+1)^2 Gram entries when the
+// least squares is global ("NCCL Gram allreduce"), Cholesky on the host.  Squares the condition number: offered for
+// completeness, TSQR stays the default.  ||b - R alpha|| from a second pass (not from b'b - g'alpha: cancellation).
+static int op_normal_equations(msp_engine *e, int kind, int s, bool global, double *alpha, double *rnorm_out) {
+  const int nc = s + 1;
+  if (nc > 9) MSP_FAIL("the normal-equations minimiser supports s <= 8");
+  const double *rhs_src = kind_is_local(kind) ? e->rhs : e->b;
+  double *bcol = e->R + (long long)s * e->ld;
+  k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, rhs_src, bcol);
+  e->launches++;
+  launch_gram(e, nc, e->R, e->dfac);
+  if (global) RC(e->comm->allreduce_sum(e->dfac, nc * nc, e->st));
+  std::vector<double> G((size_t)nc * nc), U((size_t)s * s), Gs((size_t)s * s);
+  CK(cudaMemcpyAsync(G.data(), e->dfac, sizeof(double) * nc * nc, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  for (int j = 0; j < s; j++) for (int i = 0; i <= j; i++) Gs[(size_t)j * s + i] = G[(size_t)j * nc + i];
+  if (!chol_upper(s, Gs.data(), U.data())) MSP_FAIL("normal equations: the Gram matrix is not positive definite at working precision (use the TSQR minimiser)");
+  // U^T U alpha = g, g = R^T b = last column of the augmented Gram
+  std::vector<double> y(s);
+  for (int i = 0; i < s; i++) {
+    double t = G[(size_t)s * nc + i];
+    for (int k = 0; k < i; k++) t -= U[(size_t)i * s + k] * y[k];
+    y[i] = t / U[(size_t)i * s + i];
+  }
+  for (int i = s - 1; i >= 0; i--) {
+    double t = y[i];
+    for (int k = i + 1; k < s; k++) t -= U[(size_t)k * s + i] * alpha[k];
+    alpha[i] = t / U[(size_t)i * s + i];
+  }
+  if (rnorm_out) {
+    // r = rhs - R alpha, in place in the rhs column
+    for (int j = 0; j < s; j++) e->hsc[216 + j] = -alpha[j];
+    CK(cudaMemcpyAsync(e->dsc + 216, e->hsc + 216, sizeof(double) * s, cudaMemcpyHostToDevice, e->st));
+    launch_maxpy<0>(e, s, e->R, e->ld, e->dsc + 216, bcol, e->dsc + 6, -1, 0, 0, 3);
+    RC(read_scalars(e, 6, 1));
+    e->hsc[6] = e->hsc[6] * e->hsc[6];
+    if (global) {
+      CK(cudaMemcpyAsync(e->dsc + 6, e->hsc + 6, sizeof(double), cudaMemcpyHostToDevice, e->st));
+      RC(allreduce_host(e, 6, 1));
+    }
+    *rnorm_out = std::sqrt(e->hsc[6]);
+  }
+  return 0;
+}
+
 // small dense least squares on the host: stack nfac upper factors [U_k | c_k; 0 rho_k] and solve by
 // Householder QR.  This is the root of the TSQR tree (s <= 32: a few kflop).
 static int tsqr_combine(int s, int nfac, const double *uall, double *alpha, double *resnorm) {
@@ -1074,15 +1120,17 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
       RC(exchange_sync(e));
       RC(op_push_iterate(e, t));
     }
-    if (lsqr) {
-      // the reference's minimiser, literally: LSQR on R = A S with the raw basis (utils.c:1061-1103)
+    if (lsqr || o->outer_type == 2) {
+      // the reference's minimisers, literally: LSQR on R = A S with the raw basis (utils.c:1061-1103), or the normal
+      // equations on the Gram matrix (utils.c:972-996; basis of successive corrections to keep it solvable)
       int lits = 0;
       double norm = 0.0;
-      RC(op_spmm(e, alg, s, false));
+      RC(op_spmm(e, alg, s, !lsqr));
       if (alg == MSP_ALG_SMSM_LOCAL) RC(op_update_rhs(e));
       double ln = 0.0;
       if (alg == MSP_ALG_SMSM_SEMI_LOCAL) { RC(op_resid_sumsq(e, false, 1)); RC(read_scalars(e, 1, 1)); ln = std::sqrt(e->hsc[1]); }
-      RC(op_lsqr(e, alg, s, alg == MSP_ALG_SMSM_GLOBAL, lsqr_max_it, lsqr_rtol, lsqr_abstol, alpha.data(), &norm, &lits));
+      if (lsqr) RC(op_lsqr(e, alg, s, alg == MSP_ALG_SMSM_GLOBAL, lsqr_max_it, lsqr_rtol, lsqr_abstol, alpha.data(), &norm, &lits));
+      else RC(op_normal_equations(e, alg, s, alg == MSP_ALG_SMSM_GLOBAL, alpha.data(), &norm));
       res->outer_solver_its += lits;
       RC(op_apply_alpha(e, alg, s, alpha.data()));
       if (alg == MSP_ALG_SMSM_GLOBAL) {
@@ -1737,7 +1785,7 @@ static int async_publish(msp_engine *e, int iter) {
 static int async_begin(msp_engine *e, const msp_solve_opts *o, msp_result *res, AsyncRun *run) {
   const int G = e->prob.nblocks, s = o->s;
   memset(res, 0, sizeof(*res));
-  if (o->outer_type == 1) MSP_FAIL("the LSQR minimiser is available for the synchronous variants only");
+  if (o->outer_type != 0) MSP_FAIL("the LSQR and normal-equations minimisers are available for the synchronous variants only");
   if (o->alg != MSP_ALG_AM && (s < 1 || s > e->smax)) MSP_FAIL("s exceeds the engine's basis storage");
   for (int side = 0; side < 2; side++)
     if (e->has_nb[side] && !e->peer[side].base) MSP_FAIL("neighbour window not connected");

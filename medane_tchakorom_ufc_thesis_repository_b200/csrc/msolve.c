@@ -9,7 +9,8 @@
  * like the PETSc options database does, and prints the log lines the reference's log scrapers rely on
  * (utils.c:668-729).  All numerics happen behind the C-ABI of libmsplit.so (include/msplit.h).
  *
- * Extensions: -minimizer tsqr|lsqr (default tsqr = exact least squares; lsqr = the reference's PETSc LSQR, driven by
+ * Extensions: -minimizer tsqr|lsqr|gram (default tsqr = exact least squares; gram = normal equations on R'R;
+ * lsqr = the reference's PETSc LSQR, driven by
  * -outer{K}_ksp_max_it / -outer{K}_ksp_rtol / -outer{K}_ksp_atol), -alg <iSolve name | reference binary name>, -p <depth> (3-D, poisson3DMatrix), -nblocks G
  * (default: the reference's np/npb = 2; 1 for GMRES), -devices 0,1,... (one entry per block, default: block K on
  * GPU K mod #GPUs), -max_outer N, -period a,b,... (deterministic asynchronous schedule, tests only).
@@ -179,7 +180,8 @@ int main(int argc, char **argv) {
     const char *mz = opt_find(&db, "-minimizer", NULL);
     if (mz && *mz) {
       if (!strcasecmp(mz, "lsqr")) outer_type = 1;
-      else if (strcasecmp(mz, "tsqr") && strcasecmp(mz, "qr")) { fprintf(stderr, "msolve: -minimizer %s unknown (tsqr | lsqr)\n", mz); return 2; }
+      else if (!strcasecmp(mz, "gram") || !strcasecmp(mz, "normal")) outer_type = 2;
+      else if (strcasecmp(mz, "tsqr") && strcasecmp(mz, "qr")) { fprintf(stderr, "msolve: -minimizer %s unknown (tsqr | lsqr | gram)\n", mz); return 2; }
     }
     const char *pre[] = {"outer_", "outer1_"};
     for (int i = 0; i < 2; i++) {

@@ -265,7 +265,7 @@ def make_solve_opts(alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_ou
     o.max_outer = max_outer
     o.record_history = int(record_history)
     o.profile = int(profile)
-    o.outer_type = 1 if outer_type == "lsqr" else 0
+    o.outer_type = {"tsqr": 0, "qr": 0, "lsqr": 1, "gram": 2, "normal": 2}[outer_type]
     o.outer_max_it, o.outer_rtol, o.outer_abstol = outer_max_it, outer_rtol, outer_abstol
     for i in range(_lib.MAX_BLOCKS):
         o.period[i] = periods[i] if periods and i < len(periods) else 0

@@ -368,6 +368,20 @@ def test_lsqr_minimiser_matches_oracle_lsqr(S, oracle, alg, G):
     grp.close()
 
 
+@pytest.mark.parametrize("alg,G", [("SMSM_GLOBAL", 2), ("SMSM_SEMI_LOCAL", 4), ("SMSM_LOCAL", 2)])
+def test_normal_equations_minimiser(S, oracle, alg, G):
+    """-minimizer gram (the reference's `outer_solver`: Gram matrix + s x s solve, Gram allreduce for the global variant):
+    same minimiser as the exact least squares while the basis is well conditioned."""
+    inner = dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)
+    grp = S.Group(32, 32, nblocks=G, s=4, max_restart=30)
+    res = grp.solve(alg, s=4, rtol=1e-300, inner=S.ksp_opts(**inner), max_outer=2, outer_type="gram")
+    ref = oracle.solve(alg, 32, 32, nblocks=G, s=4, rtol=1e-300, inner=inner, max_outer=2)
+    x = grp.solution()
+    assert np.linalg.norm(x - ref["x"]) <= 1e-6 * np.linalg.norm(ref["x"])
+    assert np.allclose(np.max([r["hist"] for r in res], axis=0), ref["hist"], rtol=1e-5)
+    grp.close()
+
+
 def test_modified_gram_schmidt_option(S, oracle):
     """-ksp_gmres_modifiedgramschmidt and the two CGS refinement types give the oracle's iteration counts."""
     N = 40
