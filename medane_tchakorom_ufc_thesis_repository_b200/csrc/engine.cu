@@ -757,7 +757,7 @@ static void launch_gram_nc(msp_engine *e, const double *C, double *out_dev) {
 template <int NC>
 static void launch_trsolve_nc(msp_engine *e, double *C, const double *U_dev) {
   auto k = k_right_trsolve<NC>;
-  k<<<grid_for(e->nb, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(e->nb, e->ld, C, U_dev);
+  k<<<grid_for((long long)e->nb / 2, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(e->nb, e->ld, C, U_dev);
   e->launches++;
 }
 static void launch_gram(msp_engine *e, int nc, const double *C, double *out_dev) {

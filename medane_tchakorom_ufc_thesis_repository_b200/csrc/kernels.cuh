@@ -801,24 +801,38 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_gram(int nb, long long ld, con
   }
 }
 
-// C := C U^{-1} for an upper-triangular U (NC x NC, column-major in `U`): one read+write pass, each thread owns rows.
+// C := C U^{-1} for an upper-triangular U (NC x NC, column-major in `U`): one read+write pass, two rows per thread
+// (128-bit loads/stores), reciprocal pivots precomputed in shared memory.
 template <int NC>
 __global__ void __launch_bounds__(MSPK_THREADS) k_right_trsolve(int nb, long long ld, double *__restrict__ C, const double *__restrict__ U) {
-  __shared__ double u[NC * NC];
+  __shared__ double u[NC * NC], rinv[NC];
   for (int i = threadIdx.x; i < NC * NC; i += blockDim.x) u[i] = U[i];
+  for (int i = threadIdx.x; i < NC; i += blockDim.x) rinv[i] = 1.0 / U[i * NC + i];
   __syncthreads();
-  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nb; r += (long long)gridDim.x * blockDim.x) {
-    double y[NC];
+  const long long npairs = nb >> 1;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npairs; p += (long long)gridDim.x * blockDim.x) {
+    double2 y[NC];
 #pragma unroll
-    for (int c = 0; c < NC; c++) y[c] = C[c * ld + r];
+    for (int c = 0; c < NC; c++) y[c] = ld_stream2(C + c * ld + 2 * p);
 #pragma unroll
     for (int j = 0; j < NC; j++) {
-      double t = y[j];
+      double2 t = y[j];
 #pragma unroll
-      for (int i = 0; i < j; i++) t = fma(-y[i], u[j * NC + i], t);
-      y[j] = t / u[j * NC + j];
+      for (int i = 0; i < j; i++) { t.x = fma(-y[i].x, u[j * NC + i], t.x); t.y = fma(-y[i].y, u[j * NC + i], t.y); }
+      y[j] = make_double2(t.x * rinv[j], t.y * rinv[j]);
     }
 #pragma unroll
+    for (int c = 0; c < NC; c++) __stcs(reinterpret_cast<double2 *>(C + c * ld + 2 * p), y[c]);
+  }
+  if ((nb & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long r = nb - 1;
+    double y[NC];
+    for (int c = 0; c < NC; c++) y[c] = C[c * ld + r];
+    for (int j = 0; j < NC; j++) {
+      double t = y[j];
+      for (int i = 0; i < j; i++) t = fma(-y[i], u[j * NC + i], t);
+      y[j] = t * rinv[j];
+    }
     for (int c = 0; c < NC; c++) C[c * ld + r] = y[c];
   }
 }
