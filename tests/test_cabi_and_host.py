@@ -10,6 +10,13 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def test_library_loads_and_exports_header_symbols():
     from medane_tchakorom_ufc_thesis_repository_b200 import _lib
     if not os.path.exists(_lib.LIB_PATH):
@@ -85,7 +92,7 @@ def test_two_rank_bootstrap_on_gloo(tmp_path):
     script.write_text(_WORKER)
     env = dict(os.environ, MSP_ROOT=ROOT)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                          "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)],
                          env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("worker ok") == 2
