@@ -237,6 +237,7 @@ int main(int argc, char **argv) {
   memset(&so, 0, sizeof so);
   so.alg = alg; so.s = uses_s ? s : 0; so.rtol = rtol; so.inner = inner; so.max_outer = max_outer; so.record_history = 1;
   so.outer_type = outer_type; so.outer_max_it = outer_max_it; so.outer_rtol = outer_rtol; so.outer_abstol = outer_atol;
+  so.profile = opt_flag(&db, "-log_view"); /* per-event device times, like PETSc's -log_view (events bracket every launch) */
   for (int k = 0; k < nblocks; k++) so.period[k] = periods[k];
   msp_result *res = (msp_result *)calloc((size_t)nblocks, sizeof(msp_result));
   CHECK(msp_group_solve(g, &so, res));
@@ -258,6 +259,14 @@ int main(int argc, char **argv) {
     printf("Stage I_Solver (inner GMRES solves): %f s\n", res[0].stage_inner_s);
     printf("Stage O_Solver (exchange, A*S, minimisation, convergence test): %f s\n", res[0].stage_outer_s);
     if (res[0].outer_solver_its) printf("Outer solver (LSQR) iterations: %lld\n", (long long)res[0].outer_solver_its);
+    /* self time per event in microseconds, in the layout of `-log_view ::ascii_flamegraph` (tmp/function-calling-stack:6-13) */
+    printf("total solving;I_Solver stage;KSPSolve;KSPGMRESOrthog;VecMDot %.0f\n", res[0].t_mdot_ms * 1e3);
+    printf("total solving;I_Solver stage;KSPSolve;KSPGMRESOrthog;VecMAXPY %.0f\n", res[0].t_maxpy_ms * 1e3);
+    printf("total solving;I_Solver stage;KSPSolve;MatMult %.0f\n", res[0].t_spmv_ms * 1e3);
+    printf("total solving;O_Solver stage;exchange %.0f\n", res[0].t_other_ms * 1e3);
+    if (res[0].t_mdot_ms > 0)
+      printf("[msolve] algorithmic GB/s: VecMDot %.0f  VecMAXPY(+VecNorm) %.0f  MatMult %.0f\n", res[0].b_mdot / res[0].t_mdot_ms * 1e-6,
+             res[0].b_maxpy / res[0].t_maxpy_ms * 1e-6, res[0].b_spmv / res[0].t_spmv_ms * 1e-6);
   }
   long long launches = 0;
   for (int k = 0; k < nblocks; k++) launches += (long long)res[k].kernel_launches;
