@@ -498,6 +498,58 @@ def test_cholqr_breakdown_falls_back(S, oracle):
     e.close()
 
 
+def test_operator_surface_hand_driven(S, oracle):
+    """The fine-grained operator surface (updateLocalRHS, inner_solver, the exchange, MatMatMult, the minimiser) driven
+    from the host exactly like the reference's main() does (…-minimization-global.c:288-363), against the fused
+    msp_group_solve loop and the oracle: same iterates."""
+    m, n, G, s = 32, 24, 2, 3
+    inner = dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)
+    ko = S.ksp_opts(**inner)
+    blocks = [S.Engine(m, n, block=k, nblocks=G, s=s, max_restart=30) for k in range(G)]
+    H = blocks[0].H
+    norm0 = np.sqrt(sum(np.linalg.norm(e.b) ** 2 for e in blocks))
+    hist = []
+    for outer in range(3):
+        for t in range(s):
+            for e in blocks:
+                e.updateLocalRHS()
+                e.inner_solver(ko)
+            xs = [e.x for e in blocks]                       # comm_sync_send_and_receive: boundary layers only
+            blocks[0].set_halo(1, xs[1][:H])
+            blocks[1].set_halo(0, xs[0][-H:])
+            for e in blocks:
+                e.push_iterate(t)
+        for e in blocks:
+            e.spmm_AS("SMSM_GLOBAL")
+        factors = [e.minimize_local_qr("SMSM_GLOBAL") for e in blocks]
+        alpha, rn = S.tsqr_combine(s, factors)               # every block solves the same stacked system
+        for e in blocks:
+            e.apply_alpha("SMSM_GLOBAL", alpha)
+        hist.append(rn)
+    x_hand = np.concatenate([e.x for e in blocks])
+    for e in blocks:
+        e.close()
+    grp = S.Group(m, n, nblocks=G, s=s, max_restart=30)
+    res = grp.solve("SMSM_GLOBAL", s=s, rtol=1e-300, inner=ko, max_outer=3)
+    ref = oracle.solve("SMSM_GLOBAL", m, n, nblocks=G, s=s, rtol=1e-300, inner=inner, max_outer=3)
+    assert np.allclose(hist, res[0]["hist"], rtol=1e-12) and np.allclose(hist, ref["hist"], rtol=1e-7)
+    assert np.linalg.norm(x_hand - grp.solution()) <= 1e-12 * np.linalg.norm(x_hand)
+    assert np.linalg.norm(x_hand - ref["x"]) <= 1e-8 * np.linalg.norm(x_hand)
+    assert abs(res[0]["norm0"] - norm0) <= 1e-12 * norm0
+    grp.close()
+
+
+def test_isolve_launcher(S):
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([os.path.join(root, "iSolve"), "--alg", "SMSM_LOCAL", "--np", "2", "--npb", "1", "--m", "32", "--n", "32", "--s", "3",
+                          "--rtol", "1e-3", "--inner-max-it", "5", "--inner-rtol", "1e-10"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert re.search(r"\[ Block rank 1 \] Total number of iterations \(outer_iterations \* s\) = \d+ \* 3 = \d+", out.stdout)
+    assert "Elapsed time (iterations):" in out.stdout and "Final residual norm 2 =" in out.stdout
+
+
 def test_errors(S):
     with pytest.raises(S.MsplitError):
         S.Engine(10, 10, nblocks=3)  # grid lines not divisible by the block count
