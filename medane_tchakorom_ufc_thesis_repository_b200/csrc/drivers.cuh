@@ -1,0 +1,502 @@
+// drivers.cuh — the reference drivers' outer loops: synchronous, stand-alone GMRES, block group, asynchronous (included by engine.cu).
+#pragma once
+// ------------------------------------------------------------------------------------------------
+// the drivers' outer loops (one engine = one block; comm provides barrier / allreduce)
+// ------------------------------------------------------------------------------------------------
+static int exchange_sync(msp_engine *e) {
+  // the boundary layers were already stored into the neighbours' windows by k_update_x / k_publish_boundary
+  // (class 3 of the profile = barrier + collection of the received layers; bytes = what crossed NVLink into this block)
+  e->prof_begin(3, 8.0 * e->H * ((e->has_nb[0] ? 1 : 0) + (e->has_nb[1] ? 1 : 0)));
+  int rc = e->comm->barrier(e->st);
+  if (!rc) rc = op_collect_halos(e);
+  e->prof_end();
+  return rc;
+}
+
+static int allreduce_host(msp_engine *e, int first, int n) {
+  // sum dsc[first..first+n) over blocks and bring it to hsc
+  RC(e->comm->allreduce_sum(e->dsc + first, n, e->st));
+  return read_scalars(e, first, n);
+}
+
+static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result *res) {
+  const int G = e->prob.nblocks, s = o->s;
+  const int alg = o->alg;
+  const double atol = 1e-100; // hard-coded absolute_tolerance (…-global.c:34)
+  msp_ksp_opts in = o->inner;
+  in.initial_rtol = 1; in.guess_nonzero = 1; // inner_solver utils.c:956-957
+  if (alg != MSP_ALG_SM && (s < 1 || s > e->smax)) MSP_FAIL("s exceeds the engine's basis storage");
+  const int max_outer = o->max_outer > 0 ? o->max_outer : 1000000;
+  memset(res, 0, sizeof(*res));
+  // global_norm_0 = computeFinalResidualNorm(x = 0) before the loop (…multisplitting.c:162) = ||b||; computed from b so
+  // that a call continuing from a previous iterate keeps the same reference norm
+  k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->b, 0.0, e->ws, 2, e->dsc + 0);
+  e->launches++;
+  RC(allreduce_host(e, 0, 1));
+  res->norm0 = std::sqrt(e->hsc[0]);
+  const double thr_global = std::max(atol, o->rtol * res->norm0);
+  const double thr_local = std::max(atol, (o->rtol / std::sqrt((double)G)) * 1.0 * res->norm0);
+  RC(e->comm->barrier(e->st)); // PetscBarrier before MPI_Wtime
+  cudaEvent_t ev0, ev1;
+  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  CK(cudaEventRecord(ev0, e->st));
+  const int64_t launches0 = e->launches;
+  e->prof = o->profile != 0;
+  bool done = false;
+  int sticky = 0;
+  const bool lsqr = o->outer_type == 1;
+  const int lsqr_max_it = o->outer_max_it > 0 ? o->outer_max_it : 100;
+  const double lsqr_rtol = o->outer_rtol > 0 ? o->outer_rtol : 1e-15, lsqr_abstol = o->outer_abstol > 0 ? o->outer_abstol : 1e-100;
+  typedef std::chrono::steady_clock clk;
+  auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  std::vector<double> uaug((size_t)(s + 1) * (s + 1)), alpha(std::max(s, 1));
+  if (alg == MSP_ALG_SM) RC(op_update_rhs(e)); // …multisplitting.c:164
+  while (!done && res->outer_its < max_outer) {
+    if (alg == MSP_ALG_SM) {
+      int its = 0, reason = 0;
+      auto t0 = clk::now();
+      RC(op_inner_solve(e, &in, true, &its, &reason, nullptr));
+      auto t1 = clk::now();
+      res->stage_inner_s += secs(t0, t1);
+      res->inner_its_total += its;
+      RC(exchange_sync(e));
+      RC(op_update_rhs(e));
+      RC(op_resid_sumsq(e, false, 0));
+      RC(allreduce_host(e, 0, 1));
+      const double norm = std::sqrt(e->hsc[0]);
+      res->last_norm = norm;
+      if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = norm;
+      if (norm <= thr_global) done = true;
+      res->outer_its++;
+      res->stage_outer_s += secs(t1, clk::now());
+      continue;
+    }
+    auto t_outer0 = clk::now();
+    double inner_this = 0.0;
+    for (int t = 0; t < s; t++) {
+      RC(op_update_rhs(e));
+      int its = 0, reason = 0;
+      auto t0 = clk::now();
+      RC(op_inner_solve(e, &in, true, &its, &reason, nullptr));
+      inner_this += secs(t0, clk::now());
+      res->inner_its_total += its;
+      RC(exchange_sync(e));
+      RC(op_push_iterate(e, t));
+    }
+    if (lsqr || o->outer_type == 2) {
+      // the reference's minimisers, literally: LSQR on R = A S with the raw basis (utils.c:1061-1103), or the normal
+      // equations on the Gram matrix (utils.c:972-996; basis of successive corrections to keep it solvable)
+      int lits = 0;
+      double norm = 0.0;
+      RC(op_spmm(e, alg, s, !lsqr));
+      if (alg == MSP_ALG_SMSM_LOCAL) RC(op_update_rhs(e));
+      double ln = 0.0;
+      if (alg == MSP_ALG_SMSM_SEMI_LOCAL) { RC(op_resid_sumsq(e, false, 1)); RC(read_scalars(e, 1, 1)); ln = std::sqrt(e->hsc[1]); }
+      if (lsqr) RC(op_lsqr(e, alg, s, alg == MSP_ALG_SMSM_GLOBAL, lsqr_max_it, lsqr_rtol, lsqr_abstol, alpha.data(), &norm, &lits));
+      else RC(op_normal_equations(e, alg, s, alg == MSP_ALG_SMSM_GLOBAL, alpha.data(), &norm));
+      res->outer_solver_its += lits;
+      RC(op_apply_alpha(e, alg, s, alpha.data()));
+      if (alg == MSP_ALG_SMSM_GLOBAL) {
+        res->last_norm = norm; // KSPGetResidualNorm(outer_ksp) = phibar (…-global.c:343)
+        if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = norm;
+        if (norm <= thr_global) done = true;
+      } else {
+        if (alg == MSP_ALG_SMSM_LOCAL) { RC(op_resid_sumsq(e, false, 1)); RC(read_scalars(e, 1, 1)); ln = std::sqrt(e->hsc[1]); }
+        if (ln <= thr_local) sticky = 1;
+        e->hsc[2] = sticky; e->hsc[3] = ln * ln;
+        CK(cudaMemcpyAsync(e->dsc + 2, e->hsc + 2, 16, cudaMemcpyHostToDevice, e->st));
+        RC(allreduce_host(e, 2, 2));
+        res->last_norm = ln;
+        if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = ln;
+        if ((int)std::lround(e->hsc[2]) == G) done = true;
+      }
+    } else if (alg == MSP_ALG_SMSM_GLOBAL) {
+      RC(op_spmm(e, alg, s));
+      RC(op_local_qr(e, alg, s, uaug.data()));
+      // TSQR: gather every block's factor (zero-padded allreduce = allgather), identical small solve everywhere
+      const int nn = (s + 1) * (s + 1);
+      std::vector<double> all((size_t)G * nn, 0.0);
+      if (G > 1) {
+        memcpy(all.data() + (size_t)e->prob.block * nn, uaug.data(), sizeof(double) * nn);
+        CK(cudaMemcpyAsync(e->dfac, all.data(), sizeof(double) * (size_t)G * nn, cudaMemcpyHostToDevice, e->st));
+        RC(e->comm->allreduce_sum(e->dfac, G * nn, e->st));
+        CK(cudaMemcpyAsync(all.data(), e->dfac, sizeof(double) * (size_t)G * nn, cudaMemcpyDeviceToHost, e->st));
+        CK(cudaStreamSynchronize(e->st));
+      } else {
+        all = uaug;
+      }
+      double norm = 0.0;
+      RC(tsqr_combine(s, G, all.data(), alpha.data(), &norm));
+      RC(op_apply_alpha(e, alg, s, alpha.data()));
+      res->last_norm = norm;
+      if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = norm;
+      if (norm <= thr_global) done = true;
+    } else if (alg == MSP_ALG_SMSM_SEMI_LOCAL) {
+      RC(op_spmm(e, alg, s));
+      RC(op_local_qr(e, alg, s, uaug.data()));
+      RC(tsqr_combine(s, 1, uaug.data(), alpha.data(), nullptr));
+      RC(op_resid_sumsq(e, false, 1)); // pre-minimisation x_K against the stale rhs_K (…-semi-local.c:326)
+      RC(read_scalars(e, 1, 1));
+      const double ln = std::sqrt(e->hsc[1]);
+      if (ln <= thr_local) sticky = 1;
+      RC(op_apply_alpha(e, alg, s, alpha.data()));
+      e->hsc[2] = sticky; e->hsc[3] = ln * ln;
+      CK(cudaMemcpyAsync(e->dsc + 2, e->hsc + 2, 16, cudaMemcpyHostToDevice, e->st));
+      RC(allreduce_host(e, 2, 2));
+      res->last_norm = ln;
+      if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = ln;
+      if ((int)std::lround(e->hsc[2]) == G) done = true; // comm_sync_convergence_detection comm.c:235-250
+    } else if (alg == MSP_ALG_SMSM_LOCAL) {
+      RC(op_spmm(e, alg, s));
+      RC(op_update_rhs(e));
+      RC(op_local_qr(e, alg, s, uaug.data()));
+      RC(tsqr_combine(s, 1, uaug.data(), alpha.data(), nullptr));
+      RC(op_apply_alpha(e, alg, s, alpha.data()));
+      RC(op_resid_sumsq(e, false, 1));
+      RC(read_scalars(e, 1, 1));
+      const double ln = std::sqrt(e->hsc[1]);
+      if (ln <= thr_local) sticky = 1;
+      e->hsc[2] = sticky; e->hsc[3] = ln * ln;
+      CK(cudaMemcpyAsync(e->dsc + 2, e->hsc + 2, 16, cudaMemcpyHostToDevice, e->st));
+      RC(allreduce_host(e, 2, 2));
+      res->last_norm = ln;
+      if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = ln;
+      if ((int)std::lround(e->hsc[2]) == G) done = true;
+    } else {
+      MSP_FAIL("algorithm not handled by the synchronous driver");
+    }
+    res->outer_its++;
+    res->stage_inner_s += inner_this;
+    res->stage_outer_s += secs(t_outer0, clk::now()) - inner_this;
+  }
+  RC(e->comm->barrier(e->st));
+  CK(cudaEventRecord(ev1, e->st));
+  CK(cudaEventSynchronize(ev1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ev0, ev1));
+  res->elapsed_s = ms * 1e-3;
+  res->kernel_launches = e->launches - launches0;
+  CK(cudaEventDestroy(ev0)); CK(cudaEventDestroy(ev1));
+  e->prof_collect(res);
+  e->prof = false;
+  // closing exchange + true residual + error (comm_sync_send_and_receive_final comm.c:199, utils.c:575, :1045)
+  RC(op_publish_boundary(e));
+  RC(exchange_sync(e));
+  RC(op_resid_sumsq(e, true, 0));
+  k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->x, 1.0, e->ws, 2, e->dsc + 1);
+  e->launches++;
+  RC(allreduce_host(e, 0, 2));
+  res->final_residual = std::sqrt(e->hsc[0]);
+  res->error = std::sqrt(e->hsc[1]);
+  return 0;
+}
+
+// gmres_solution.c:50-85
+static int engine_gmres(msp_engine *e, const msp_ksp_opts *o, msp_result *res) {
+  memset(res, 0, sizeof(*res));
+  if (e->prob.nblocks != 1) MSP_FAIL("stand-alone GMRES runs on a single block");
+  CK(cudaMemsetAsync(e->x, 0, sizeof(double) * e->ld, e->st));
+  CK(cudaMemcpyAsync(e->rhs, e->b, sizeof(double) * e->ld, cudaMemcpyDeviceToDevice, e->st));
+  k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->b, 0.0, e->ws, 2, e->dsc + 0);
+  RC(read_scalars(e, 0, 1));
+  res->norm0 = std::sqrt(e->hsc[0]);
+  msp_ksp_opts in = *o;
+  in.guess_nonzero = 0;
+  cudaEvent_t ev0, ev1;
+  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  CK(cudaEventRecord(ev0, e->st));
+  const int64_t l0 = e->launches;
+  RC(op_inner_solve(e, &in, false, &res->gmres_its, &res->gmres_reason, &res->gmres_rnorm));
+  CK(cudaEventRecord(ev1, e->st));
+  CK(cudaEventSynchronize(ev1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ev0, ev1));
+  res->elapsed_s = ms * 1e-3;
+  res->kernel_launches = e->launches - l0;
+  CK(cudaEventDestroy(ev0)); CK(cudaEventDestroy(ev1));
+  res->outer_its = res->gmres_its;
+  res->last_norm = res->gmres_rnorm;
+  RC(op_resid_sumsq(e, true, 0));
+  k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->x, 1.0, e->ws, 2, e->dsc + 1);
+  RC(read_scalars(e, 0, 2));
+  res->final_residual = std::sqrt(e->hsc[0]);
+  res->error = std::sqrt(e->hsc[1]);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// group: all blocks in one process
+// ------------------------------------------------------------------------------------------------
+struct msp_group {
+  int G = 0;
+  std::vector<msp_engine *> eng;
+  LocalShared *sh = nullptr;
+};
+
+static int group_wire(msp_group *g) {
+  for (int k = 0; k < g->G; k++) {
+    msp_engine *e = g->eng[k];
+    if (e->own_comm && e->comm) delete e->comm;
+    e->comm = new LocalComm(g->sh, k); e->own_comm = true;
+    e->grp = g;
+    for (int side = 0; side < 2; side++) {
+      int nbk = side == 0 ? k - 1 : k + 1;
+      if (nbk < 0 || nbk >= g->G) continue;
+      msp_engine *p = g->eng[nbk];
+      if (p->device != e->device) {
+        cudaSetDevice(e->device);
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, e->device, p->device);
+        if (!can) MSP_FAIL("peer access between the two GPUs is not available");
+        cudaError_t er = cudaDeviceEnablePeerAccess(p->device, 0);
+        if (er != cudaSuccess && er != cudaErrorPeerAccessAlreadyEnabled) MSP_FAIL("cudaDeviceEnablePeerAccess failed");
+        cudaGetLastError();
+      }
+      e->peer[side] = p->win; e->peer_ipc[side] = false;
+    }
+    for (int J = 0; J < g->G; J++) {
+      if (J == k) continue;
+      msp_engine *p = g->eng[J];
+      if (p->device != e->device) {
+        cudaSetDevice(e->device);
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, e->device, p->device);
+        if (!can) MSP_FAIL("peer access between the two GPUs is not available");
+        cudaError_t er = cudaDeviceEnablePeerAccess(p->device, 0);
+        if (er != cudaSuccess && er != cudaErrorPeerAccessAlreadyEnabled) MSP_FAIL("cudaDeviceEnablePeerAccess failed");
+        cudaGetLastError();
+      }
+      e->peer_any[J] = p->win; e->peer_any_ipc[J] = false;
+    }
+  }
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// asynchronous variants (…multisplitting_prime.c:321-393, …-minimization-{global,semi-local,local}_prime.c)
+// ------------------------------------------------------------------------------------------------
+struct AsyncRun {
+  int iters = 0;         // number_of_iterations
+  int inner_outer = 0;   // number_of_inner_times_outer_iterations
+  int state = 0;
+  double thr_local = 0;
+  double last_norm = 0;
+  std::vector<double> uaug, alpha, all;
+};
+
+static int slot_of_side(const msp_engine *e, int side) { return e->has_nb[0] ? side : 0; }
+
+// comm_async_probe_and_receive_prime comm.c:455-529 for both neighbours
+static int async_probe(msp_engine *e) {
+  for (int side = 0; side < 2; side++) {
+    if (!e->has_nb[side]) continue;
+    k_async_probe<<<1, 32, 0, e->st>>>(e->win.hdr(side), e->cd, slot_of_side(e, side), e->aint + side, e->dec + side);
+    k_async_copy<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->dec + side, e->H, e->win.halo(side, 0), e->win.halo(side, 1), e->halo[side]);
+    e->launches += 2;
+  }
+  return 0;
+}
+// comm_async_test_and_send_prime comm.c:531-554: P2P store of the boundary layers + header release
+static int async_publish(msp_engine *e, int iter) {
+  for (int side = 0; side < 2; side++) {
+    if (!e->peer[side].base) continue;
+    const int q = ++e->async_sent[side];
+    // my first layer goes to the lower neighbour's "hi" window, my last layer to the upper neighbour's "lo" window
+    double *dst = e->peer[side].halo(1 - side, q & 1);
+    k_publish_boundary<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->nb, e->H, e->x, side == 0 ? dst : nullptr, side == 1 ? dst : nullptr);
+    k_async_release<<<1, 32, 0, e->st>>>(e->peer[side].hdr(1 - side), e->cd, iter, q);
+    e->launches += 2;
+  }
+  return 0;
+}
+
+static int async_begin(msp_engine *e, const msp_solve_opts *o, msp_result *res, AsyncRun *run) {
+  const int G = e->prob.nblocks, s = o->s;
+  memset(res, 0, sizeof(*res));
+  if (o->outer_type != 0) MSP_FAIL("the LSQR and normal-equations minimisers are available for the synchronous variants only");
+  if (o->alg != MSP_ALG_AM && (s < 1 || s > e->smax)) MSP_FAIL("s exceeds the engine's basis storage");
+  for (int side = 0; side < 2; side++)
+    if (e->has_nb[side] && !e->peer[side].base) MSP_FAIL("neighbour window not connected");
+  k_cd_init<<<1, 32, 0, e->st>>>(e->cd, e->prob.block, G, e->win.mailbox(), e->peer[0].base ? e->peer[0].mailbox() : nullptr,
+                                 e->peer[1].base ? e->peer[1].mailbox() : nullptr, e->win.hdr(0), e->win.hdr(1), e->aint);
+  k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->b, 0.0, e->ws, 2, e->dsc + 0);
+  e->launches += 2;
+  RC(allreduce_host(e, 0, 1));
+  res->norm0 = std::sqrt(e->hsc[0]);
+  run->thr_local = std::max(1e-100, (o->rtol / std::sqrt((double)G)) * 1.0 * res->norm0);
+  run->uaug.assign((size_t)(s + 1) * (s + 1), 0.0);
+  run->alpha.assign(std::max(s, 1), 0.0);
+  std::fill(e->fcache_seq.begin(), e->fcache_seq.end(), 0);
+  RC(op_update_rhs(e)); // …multisplitting_prime.c:315
+  return 0;
+}
+
+// one pass of the do { } while (state != FINISHED) body of this block
+static int async_step(msp_engine *e, const msp_solve_opts *o, msp_result *res, AsyncRun *run) {
+  const int alg = o->alg, s = o->s, G = e->prob.nblocks;
+  msp_ksp_opts in = o->inner;
+  in.initial_rtol = 1; in.guess_nonzero = 1;
+  int its = 0, reason = 0;
+  if (alg == MSP_ALG_AM) {
+    RC(async_probe(e));
+    RC(op_update_rhs(e));
+    RC(op_inner_solve(e, &in, false, &its, &reason, nullptr));
+    res->inner_its_total += its;
+    RC(async_publish(e, run->iters));
+    RC(op_resid_sumsq(e, false, 1));
+  } else {
+    for (int t = 0; t < s; t++) {
+      RC(async_probe(e));
+      RC(op_update_rhs(e));
+      RC(op_inner_solve(e, &in, false, &its, &reason, nullptr));
+      res->inner_its_total += its;
+      RC(async_publish(e, run->inner_outer));
+      RC(async_probe(e));
+      RC(op_push_iterate(e, t));
+      run->inner_outer++;
+    }
+    if (alg == MSP_ALG_AMAM_GLOBAL) {
+      RC(op_spmm(e, alg, s));
+      RC(op_local_qr(e, alg, s, run->uaug.data()));
+      const int nn = (s + 1) * (s + 1), fs = e->win.fslot;
+      // publish my TSQR factor to every block (replaces the R-slab Isend, comm.c:330-347), newest wins
+      if (G > 1) {
+        std::vector<double> slot(fs, 0.0);
+        const double q = (double)(++e->factor_sent);
+        slot[0] = q; slot[fs - 1] = q;
+        memcpy(slot.data() + 1, run->uaug.data(), sizeof(double) * nn);
+        for (int J = 0; J < G; J++)
+          if (J != e->prob.block && e->peer_any[J].base)
+            CK(cudaMemcpyAsync(e->peer_any[J].factor(e->prob.block), slot.data(), sizeof(double) * fs, cudaMemcpyHostToDevice, e->st));
+        CK(cudaStreamSynchronize(e->st));
+        // newest factors the others have published so far (comm_async_probe_and_receive_min comm.c:288-328)
+        std::vector<double> mine((size_t)G * fs);
+        CK(cudaMemcpyAsync(mine.data(), e->win.factor(0), sizeof(double) * (size_t)G * fs, cudaMemcpyDeviceToHost, e->st));
+        CK(cudaStreamSynchronize(e->st));
+        for (int J = 0; J < G; J++) {
+          if (J == e->prob.block) continue;
+          const double *sl = mine.data() + (size_t)J * fs;
+          if (sl[0] > 0 && sl[0] == sl[fs - 1] && (int)sl[0] != e->fcache_seq[J]) {
+            memcpy(e->fcache.data() + (size_t)J * fs, sl, sizeof(double) * fs);
+            e->fcache_seq[J] = (int)sl[0];
+          }
+        }
+      }
+      run->all.clear();
+      int nfac = 0;
+      for (int J = 0; J < G; J++) {
+        const double *f = nullptr;
+        if (J == e->prob.block) f = run->uaug.data();
+        else if (e->fcache_seq[J] > 0) f = e->fcache.data() + (size_t)J * fs + 1;
+        if (f) { run->all.insert(run->all.end(), f, f + nn); nfac++; }
+      }
+      RC(tsqr_combine(s, nfac, run->all.data(), run->alpha.data(), nullptr));
+      RC(op_apply_alpha(e, alg, s, run->alpha.data()));
+      RC(op_resid_sumsq(e, true, 1)); // ||b_K - A_K,: x_min|| (…-global_prime.c:436-437)
+    } else if (alg == MSP_ALG_AMAM_SEMI_LOCAL) {
+      RC(op_spmm(e, alg, s));
+      RC(op_local_qr(e, alg, s, run->uaug.data()));
+      RC(tsqr_combine(s, 1, run->uaug.data(), run->alpha.data(), nullptr));
+      RC(op_apply_alpha(e, alg, s, run->alpha.data()));
+      RC(op_resid_sumsq(e, true, 1));
+    } else {
+      RC(op_spmm(e, alg, s));
+      RC(op_update_rhs(e));
+      RC(op_local_qr(e, alg, s, run->uaug.data()));
+      RC(tsqr_combine(s, 1, run->uaug.data(), run->alpha.data(), nullptr));
+      RC(op_apply_alpha(e, alg, s, run->alpha.data()));
+      RC(op_resid_sumsq(e, false, 1));
+    }
+  }
+  // root of the block: UnderThreshold + convergence detection state machine on the device
+  k_cd_step<<<1, 32, 0, e->st>>>(e->cd, 0, e->dsc + 1, run->thr_local);
+  e->launches++;
+  CK(cudaMemcpyAsync(e->hsc + 48, e->cd, 8, cudaMemcpyDeviceToHost, e->st));
+  RC(read_scalars(e, 1, 1));
+  int hs[2];
+  memcpy(hs, e->hsc + 48, 8);
+  run->state = hs[0];
+  run->last_norm = std::sqrt(e->hsc[1]);
+  run->iters++;
+  res->last_norm = run->last_norm;
+  if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = run->last_norm;
+  return 0;
+}
+
+static int async_finish(msp_engine *e, msp_result *res, AsyncRun *run) {
+  res->outer_its = run->iters;
+  // closing synchronous exchange + true residual + error (…multisplitting_prime.c:404-420)
+  RC(op_publish_boundary(e));
+  RC(exchange_sync(e));
+  RC(op_resid_sumsq(e, true, 0));
+  k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->x, 1.0, e->ws, 2, e->dsc + 1);
+  e->launches++;
+  RC(allreduce_host(e, 0, 2));
+  res->final_residual = std::sqrt(e->hsc[0]);
+  res->error = std::sqrt(e->hsc[1]);
+  return 0;
+}
+
+// free-running: what each process (or each block thread) executes
+static int engine_solve_async(msp_engine *e, const msp_solve_opts *o, msp_result *res) {
+  AsyncRun run;
+  RC(async_begin(e, o, res, &run));
+  RC(e->comm->barrier(e->st));
+  const int max_outer = o->max_outer > 0 ? o->max_outer : 1000000;
+  const int64_t l0 = e->launches;
+  auto t0 = std::chrono::steady_clock::now();
+  while (run.state != 3 && run.iters < max_outer) RC(async_step(e, o, res, &run));
+  CK(cudaStreamSynchronize(e->st));
+  res->elapsed_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  res->kernel_launches = e->launches - l0;
+  RC(e->comm->barrier(e->st));
+  return async_finish(e, res, &run);
+}
+
+static int engine_solve_async_group(msp_group *g, const msp_solve_opts *o, msp_result *res) {
+  const int G = g->G;
+  bool scheduled = false;
+  for (int k = 0; k < G; k++) scheduled |= (o->period[k] > 0);
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> errs(G);
+  if (!scheduled) {
+    std::vector<std::thread> th;
+    for (int k = 0; k < G; k++)
+      th.emplace_back([&, k] {
+        cudaSetDevice(g->eng[k]->device);
+        rcs[k] = engine_solve_async(g->eng[k], o, &res[k]);
+        if (rcs[k]) errs[k] = g_err;
+      });
+    for (auto &t : th) t.join();
+    for (int k = 0; k < G; k++) if (rcs[k]) { g_err = errs[k]; return rcs[k]; }
+    return 0;
+  }
+  // deterministic schedule (tests): block K runs one step at tick t iff t % period[K] == 0, blocks in index order;
+  // collective phases (norm0, closing exchange) still need one thread per block
+  std::vector<AsyncRun> runs(G);
+  auto par_all = [&](auto fn) {
+    std::vector<std::thread> th;
+    for (int k = 0; k < G; k++)
+      th.emplace_back([&, k] { cudaSetDevice(g->eng[k]->device); rcs[k] = fn(k); if (rcs[k]) errs[k] = g_err; });
+    for (auto &t : th) t.join();
+    for (int k = 0; k < G; k++) if (rcs[k]) { g_err = errs[k]; return rcs[k]; }
+    return 0;
+  };
+  RC(par_all([&](int k) { int rc = async_begin(g->eng[k], o, &res[k], &runs[k]); if (!rc) rc = g->eng[k]->comm->barrier(g->eng[k]->st); return rc; }));
+  const long long max_ticks = (long long)(o->max_outer > 0 ? o->max_outer : 1000000) * 64;
+  int nfin = 0;
+  for (long long tick = 0; nfin < G && tick < max_ticks; tick++) {
+    for (int k = 0; k < G; k++) {
+      const int per = o->period[k] > 0 ? o->period[k] : 1;
+      if (tick % per || runs[k].state == 3) continue;
+      cudaSetDevice(g->eng[k]->device);
+      RC(async_step(g->eng[k], o, &res[k], &runs[k]));
+      CK(cudaStreamSynchronize(g->eng[k]->st));
+      if (runs[k].state == 3) nfin++;
+    }
+  }
+  if (nfin < G) MSP_FAIL("asynchronous schedule cap reached before every block finished");
+  return par_all([&](int k) { return async_finish(g->eng[k], &res[k], &runs[k]); });
+}
+

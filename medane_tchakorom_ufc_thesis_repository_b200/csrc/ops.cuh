@@ -1,0 +1,518 @@
+// ops.cuh — the operator surface on one block: rhs update, inner GMRES solve, exchange, A*S, minimisers (included by engine.cu).
+#pragma once
+// ------------------------------------------------------------------------------------------------
+// operator surface
+// ------------------------------------------------------------------------------------------------
+static int op_update_rhs(msp_engine *e) {
+  if (e->nbrow == 0) return 0;
+  k_update_rhs<<<grid_for(e->nbrow), MSPK_THREADS, 0, e->st>>>(e->nbrow, e->brow, e->nb, e->W, e->H, e->ld, e->ecol, e->eval,
+                                                               e->has_nb[0] ? e->halo[0] : nullptr, e->has_nb[1] ? e->halo[1] : nullptr,
+                                                               e->b, e->rhs);
+  e->launches++;
+  return 0;
+}
+
+// sum of squares of (rhs - A_KK x) into dsc[slot]; strip variant: (b - A_K,: [halo|x|halo])
+static int op_resid_sumsq(msp_engine *e, bool strip, int dsc_slot) {
+  SpmvArgs a = spmv_args(e, e->x, e->Wb[1]);
+  a.b = strip ? e->b : e->rhs;
+  if (strip) {
+    a.lo = e->has_nb[0] ? e->halo[0] : nullptr; a.hi = e->has_nb[1] ? e->halo[1] : nullptr;
+    launch_spmv_w<1, true, false, true>(e, a, 1, nullptr);
+  } else {
+    launch_spmv_w<0, true, false, true>(e, a, 1, nullptr);
+  }
+  CK(cudaMemcpyAsync(e->dsc + dsc_slot, e->ws.partial + 1 * MSPK_MAX_PART + MSPK_MAX_PART - 1, sizeof(double), cudaMemcpyDeviceToDevice, e->st));
+  return 0;
+}
+
+static int read_scalars(msp_engine *e, int first, int n) {
+  CK(cudaMemcpyAsync(e->hsc + first, e->dsc + first, sizeof(double) * n, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+// inner_solver utils.c:950-970 -> KSPSolve_GMRES.  One host synchronisation per
+// restart cycle; inside a cycle every decision is taken on the device.
+static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, int *its_out, int *reason_out, double *rnorm_out) {
+  if (o->restart < 1 || o->restart > e->prob.max_restart) MSP_FAIL("restart exceeds max_restart of the engine");
+  const bool guess_zero = !o->guess_nonzero;
+  double *bnorm_sq = nullptr;
+  if (!guess_zero && !o->initial_rtol) {
+    k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->rhs, 0.0, e->ws, 2, e->dsc + 8);
+    e->launches++;
+    bnorm_sq = e->dsc + 8;
+  }
+  k_ctl_begin<<<1, 32, 0, e->st>>>(e->ctl, o->restart, o->max_it, o->min_it, o->initial_rtol, guess_zero ? 1 : 0, o->cgs_refine, o->rtol,
+                                   o->abstol, o->divtol, bnorm_sq);
+  e->launches++;
+  int itcount = 0;
+  bool first = true;
+  struct { int its, it, reason, active; } hc{};
+  double *peer_lo = (publish && e->peer[0].base) ? e->peer[0].halo(1, e->par) : nullptr; // lower neighbour's "hi" window
+  double *peer_hi = (publish && e->peer[1].base) ? e->peer[1].halo(0, e->par) : nullptr; // upper neighbour's "lo" window
+  while (true) {
+    const int nsteps = std::min(o->restart, o->max_it - itcount);
+    const bool from_rhs = first && guess_zero;
+    // everything one restart cycle enqueues: prologue, nsteps Arnoldi steps, solution update, 16-byte status read-back
+    auto enqueue_cycle = [&]() -> int {
+      // The Krylov basis is stored UN-normalised: vtilde_0 = r, vtilde_(it+1) = orthogonalised A v_it, with
+      // v_j = vtilde_j * inv_arr[j]: the SpMV scales its gathered input (bit-identical to a stored normalised vector),
+      // MDot scales the reduced value and MAXPY / the solution update fold inv_j into their coefficients.  This
+      // removes VecNormalize's write pass (K5) and the scratch vectors from the Arnoldi step.
+      // ---- cycle prologue: vtilde_0 = rhs - A x (or rhs), ||r|| and the cycle-begin logic on the device ----
+      double *V0 = e->V;
+      if (from_rhs) {
+        k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, e->rhs, V0);
+        k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->rhs, 0.0, e->ws, 2, e->dsc + 9);
+        k_ctl_cycle_begin_from<<<1, 32, 0, e->st>>>(e->ctl, e->dsc + 9);
+        e->launches += 3;
+      } else {
+        SpmvArgs a = spmv_args(e, e->x, V0);
+        a.b = e->rhs;
+        launch_spmv_w<0, true, false, true>(e, a, 0, e->ctl);
+      }
+      double *lhh = reinterpret_cast<double *>(reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, lhh));
+      const double *invs = reinterpret_cast<const double *>(reinterpret_cast<const char *>(e->ctl) + offsetof(GmresCtl, inv_arr));
+      for (int it = 0; it < nsteps; it++) {
+        // w = A v_it (K1), reading vtilde_it scaled on the fly, written straight into the slot of vtilde_(it+1)
+        double *w = e->V + (long long)(it + 1) * e->ld;
+        SpmvArgs a = spmv_args(e, e->V + (long long)it * e->ld, w);
+        a.guard_it = it;
+        launch_spmv_w<0, false, true, false>(e, a, 0, nullptr);
+        if (o->mgs) {
+          // -ksp_gmres_modifiedgramschmidt: it+1 sequential (dot, axpy) pairs; the last axpy closes the step
+          for (int j = 0; j <= it; j++) {
+            const double *vj = e->V + (long long)j * e->ld;
+            launch_mdot(e, 1, vj, e->ld, w, lhh + j, -1.0, it, 0, invs + j);
+            if (j < it) launch_maxpy<0>(e, 1, vj, e->ld, lhh + j, w, nullptr, it, 0, 0, 3, invs + j);
+            else launch_maxpy<1>(e, 1, vj, e->ld, lhh + j, w, nullptr, it, 0, 0, 0, invs + j);
+          }
+          continue;
+        }
+        // classical Gram-Schmidt: lhh = -V^T w (K3); w += V lhh, ||w|| (K4+K5), Hessenberg + test (K6)
+        launch_mdot(e, it + 1, e->V, e->ld, w, lhh, -1.0, it, 0, invs);
+        launch_maxpy<1>(e, it + 1, e->V, e->ld, lhh, w, nullptr, it, 0, 0, 0, invs);
+        if (o->cgs_refine) {
+          launch_mdot(e, it + 1, e->V, e->ld, w, lhh, -1.0, it, 1, invs);
+          launch_maxpy<1>(e, it + 1, e->V, e->ld, lhh, w, nullptr, it, 1, 1, 0, invs);
+        }
+      }
+      // ---- KSPGMRESBuildSoln + boundary publication ----
+      k_build_soln_coef<<<1, 32, 0, e->st>>>(e->ctl);
+      UpdateXArgs u{};
+      u.nb = e->nb; u.H = e->H; u.ld = e->ld; u.V = e->V; u.x = e->x; u.ctl = e->ctl; u.peer_lo = peer_lo; u.peer_hi = peer_hi;
+      k_update_x<<<grid_for(e->nb, 8), MSPK_THREADS, 0, e->st>>>(u);
+      e->launches += 2;
+      CK(cudaMemcpyAsync(e->hsc + 32, reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, its), 16, cudaMemcpyDeviceToHost, e->st));
+      return 0;
+    };
+    if (e->use_graphs && !e->prof) {
+      const msp_engine::CycleKey key(nsteps, o->cgs_refine + 4 * (o->mgs ? 1 : 0), from_rhs ? 1 : 0, (const void *)e->V, (const void *)peer_lo, (const void *)peer_hi);
+      auto itg = e->cycle_graphs.find(key);
+      if (itg == e->cycle_graphs.end()) {
+        const int64_t l0 = e->launches;
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_cycle();
+        cudaError_t ce = cudaStreamEndCapture(e->st, &graph);
+        if (rc || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); if (!rc) MSP_FAIL(std::string("stream capture failed: ") + cudaGetErrorString(ce)); return rc; }
+        msp_engine::CycleGraph cg{nullptr, (int)(e->launches - l0)};
+        e->launches = l0;
+        ce = cudaGraphInstantiate(&cg.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) MSP_FAIL(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+        if (e->cycle_graphs.size() > 256) { for (auto &kv : e->cycle_graphs) cudaGraphExecDestroy(kv.second.exec); e->cycle_graphs.clear(); }
+        itg = e->cycle_graphs.emplace(key, cg).first;
+      }
+      CK(cudaGraphLaunch(itg->second.exec, e->st));
+      e->launches += itg->second.launches;
+    } else {
+      RC(enqueue_cycle());
+    }
+    first = false;
+    CK(cudaStreamSynchronize(e->st));
+    memcpy(&hc, e->hsc + 32, 16);
+    itcount += hc.it;
+    if (hc.reason) break;
+    if (itcount >= o->max_it) { hc.reason = MSP_DIVERGED_ITS; break; }
+  }
+  if (its_out) *its_out = hc.its;
+  if (reason_out) *reason_out = hc.reason;
+  if (rnorm_out) {
+    CK(cudaMemcpyAsync(e->hsc + 40, reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, ksp_rnorm), 8, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    *rnorm_out = e->hsc[40];
+  }
+  return 0;
+}
+
+// after the synchronising barrier: copy the freshly received boundary layers into the private halos
+static int op_collect_halos(msp_engine *e) {
+  for (int side = 0; side < 2; side++)
+    if (e->has_nb[side])
+      CK(cudaMemcpyAsync(e->halo[side], e->win.halo(side, e->par), sizeof(double) * e->H, cudaMemcpyDeviceToDevice, e->st));
+  e->par ^= 1;
+  return 0;
+}
+static int op_publish_boundary(msp_engine *e) {
+  double *peer_lo = e->peer[0].base ? e->peer[0].halo(1, e->par) : nullptr;
+  double *peer_hi = e->peer[1].base ? e->peer[1].halo(0, e->par) : nullptr;
+  if (!peer_lo && !peer_hi) return 0;
+  k_publish_boundary<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->nb, e->H, e->x, peer_lo, peer_hi);
+  e->launches++;
+  return 0;
+}
+
+static int op_push_iterate(msp_engine *e, int t) {
+  if (t < 0 || t >= e->smax) MSP_FAIL("basis index out of range");
+  k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, e->x, e->S + (long long)t * e->ld);
+  e->launches++;
+  CK(cudaMemcpyAsync(e->Slo + (size_t)t * e->H, e->halo[0], sizeof(double) * e->H, cudaMemcpyDeviceToDevice, e->st));
+  CK(cudaMemcpyAsync(e->Shi + (size_t)t * e->H, e->halo[1], sizeof(double) * e->H, cudaMemcpyDeviceToDevice, e->st));
+  return 0;
+}
+
+// kind: MSP_ALG_*_GLOBAL / SEMI_LOCAL use the strip with stored boundaries, *_LOCAL uses A_KK
+static bool kind_is_local(int kind) { return kind == MSP_ALG_SMSM_LOCAL || kind == MSP_ALG_AMAM_LOCAL; }
+
+static int op_spmm(msp_engine *e, int kind, int s, bool diff_basis = true) {
+  // basis of successive corrections (same span as the iterates, far better conditioned); the LSQR path keeps the
+  // reference's raw basis [x^1 .. x^s]
+  if (diff_basis) { k_diff_basis<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, s, e->ld, e->S); e->launches++; }
+  if (diff_basis && !kind_is_local(kind)) {
+    if (e->has_nb[0]) { k_diff_basis<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->H, s, e->H, e->Slo); e->launches++; }
+    if (e->has_nb[1]) { k_diff_basis<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->H, s, e->H, e->Shi); e->launches++; }
+  }
+  SpmmArgs a{};
+  a.nb = e->nb; a.W = e->W; a.H = e->H; a.s = s; a.ld = e->ld; a.lds = e->ld; a.ecol = e->ecol; a.eval = e->eval;
+  a.S = e->S; a.R = e->R;
+  const bool local = kind_is_local(kind);
+  a.Slo = (!local && e->has_nb[0]) ? e->Slo : nullptr;
+  a.Shi = (!local && e->has_nb[1]) ? e->Shi : nullptr;
+  const int g = grid_for(e->nb, 8);
+  for (int c0 = 0; c0 < s;) {
+    int nc = std::min(8, s - c0);
+    // chunk sizes 8,5,4,2,1 cover every s with few passes over the matrix
+    int use = nc >= 8 ? 8 : nc >= 5 ? 5 : nc >= 4 ? 4 : nc >= 2 ? 2 : 1;
+#define SPMM_CASE(N)                                                                                          \
+  case N:                                                                                                     \
+    if (local) k_spmm_ell<0, N><<<g, MSPK_THREADS, 0, e->st>>>(a, c0);                                        \
+    else k_spmm_ell<1, N><<<g, MSPK_THREADS, 0, e->st>>>(a, c0);                                              \
+    break;
+    switch (use) { SPMM_CASE(8) SPMM_CASE(5) SPMM_CASE(4) SPMM_CASE(2) SPMM_CASE(1) }
+#undef SPMM_CASE
+    e->launches++;
+    c0 += use;
+  }
+  return 0;
+}
+
+// upper Cholesky factor of a symmetric NC x NC matrix given by its upper triangle (column-major); false on breakdown
+static bool chol_upper(int nc, const double *G, double *U) {
+  std::fill(U, U + nc * nc, 0.0);
+  double dmax = 0.0;
+  for (int j = 0; j < nc; j++) dmax = std::max(dmax, G[j * nc + j]);
+  for (int j = 0; j < nc; j++) {
+    for (int i = 0; i <= j; i++) {
+      double t = G[j * nc + i];
+      for (int k = 0; k < i; k++) t -= U[i * nc + k] * U[j * nc + k];
+      if (i < j) U[j * nc + i] = t / U[i * nc + i];
+      else {
+        if (!(t > 1e-13 * dmax)) return false; // not safely positive definite at working precision
+        U[j * nc + j] = std::sqrt(t);
+      }
+    }
+  }
+  return true;
+}
+
+template <int NC>
+static void launch_gram_nc(msp_engine *e, const double *C, double *out_dev) {
+  auto k = k_gram<NC>;
+  k<<<grid_for((long long)e->nb / 2, std::min(resident_blocks_per_sm(k), 4)), MSPK_THREADS, 0, e->st>>>(e->nb, e->ld, C, e->gram_partial, e->ws.counter + 40, out_dev);
+  e->launches++;
+}
+template <int NC>
+static void launch_trsolve_nc(msp_engine *e, double *C, const double *U_dev) {
+  auto k = k_right_trsolve<NC>;
+  k<<<grid_for((long long)e->nb / 2, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(e->nb, e->ld, C, U_dev);
+  e->launches++;
+}
+static void launch_gram(msp_engine *e, int nc, const double *C, double *out_dev) {
+  switch (nc) {
+    case 2: launch_gram_nc<2>(e, C, out_dev); break; case 3: launch_gram_nc<3>(e, C, out_dev); break;
+    case 4: launch_gram_nc<4>(e, C, out_dev); break; case 5: launch_gram_nc<5>(e, C, out_dev); break;
+    case 6: launch_gram_nc<6>(e, C, out_dev); break; case 7: launch_gram_nc<7>(e, C, out_dev); break;
+    case 8: launch_gram_nc<8>(e, C, out_dev); break; default: launch_gram_nc<9>(e, C, out_dev); break;
+  }
+}
+static void launch_trsolve(msp_engine *e, int nc, double *C, const double *U_dev) {
+  switch (nc) {
+    case 2: launch_trsolve_nc<2>(e, C, U_dev); break; case 3: launch_trsolve_nc<3>(e, C, U_dev); break;
+    case 4: launch_trsolve_nc<4>(e, C, U_dev); break; case 5: launch_trsolve_nc<5>(e, C, U_dev); break;
+    case 6: launch_trsolve_nc<6>(e, C, U_dev); break; case 7: launch_trsolve_nc<7>(e, C, U_dev); break;
+    case 8: launch_trsolve_nc<8>(e, C, U_dev); break; default: launch_trsolve_nc<9>(e, C, U_dev); break;
+  }
+}
+
+// CGS2 leaf (classical Gram-Schmidt with reorthogonalisation, the Arnoldi kernels K3, K4+K5) on the nc columns at e->R
+static int local_qr_cgs2(msp_engine *e, int nc, std::vector<double> &U) {
+  U.assign((size_t)nc * nc, 0.0);
+  for (int c = 0; c < nc; c++) {
+    double *q = e->R + (long long)c * e->ld;
+    if (c > 0) {
+      launch_mdot(e, c, e->R, e->ld, q, e->dsc + 64, -1.0, -1, 0);
+      launch_maxpy<0>(e, c, e->R, e->ld, e->dsc + 64, q, e->dsc + 200, -1, 0, 0, 3);
+      launch_mdot(e, c, e->R, e->ld, q, e->dsc + 128, -1.0, -1, 0);
+      launch_maxpy<0>(e, c, e->R, e->ld, e->dsc + 128, q, e->dsc + 200, -1, 0, 0, 3);
+    } else {
+      launch_maxpy<0>(e, 0, e->R, e->ld, e->dsc + 64, q, e->dsc + 200, -1, 0, 0, 3);
+    }
+    k_scale_by_inv<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->dsc + 200, q);
+    e->launches++;
+    CK(cudaMemcpyAsync(e->hsc + 64, e->dsc + 64, sizeof(double) * 140, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    for (int j = 0; j < c; j++) U[(size_t)c * nc + j] = -(e->hsc[64 + j] + e->hsc[128 + j]);
+    U[(size_t)c * nc + c] = e->hsc[200];
+  }
+  return 0;
+}
+
+// TSQR leaf: the (s+1)x(s+1) upper factor of [R_K | rhs] (column-major, to the host).
+//  * s <= 8: CholeskyQR2 — Gram contraction (K9, one pass), Cholesky on the host, C := C U1^{-1} (one pass), Gram again,
+//    U = U2 U1: 24 n (s+1) bytes instead of the ~16 n (s+1)(s+3) of Gram-Schmidt, and as accurate as Householder QR
+//    while cond([R|rhs]) < ~1e7; a Cholesky breakdown falls back to
+//  * CGS2 with the Arnoldi kernels (any s, any conditioning), continuing from whatever basis is in place.
+static int op_local_qr(msp_engine *e, int kind, int s, double *u_aug /* host (s+1)^2 */) {
+  const int nc = s + 1;
+  const double *rhs_src = kind_is_local(kind) ? e->rhs : e->b;
+  k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, rhs_src, e->R + (long long)s * e->ld);
+  e->launches++;
+  std::vector<double> U, U1, U2, G((size_t)nc * nc, 0.0);
+  bool have_u1 = false;
+  if (e->use_cholqr && nc >= 2 && nc <= 9) {
+    U1.assign((size_t)nc * nc, 0.0); U2.assign((size_t)nc * nc, 0.0);
+    double *Gdev = e->dfac; // idle between TSQR gathers; (smax+1)^2 doubles fit
+    launch_gram(e, nc, e->R, Gdev);
+    CK(cudaMemcpyAsync(G.data(), Gdev, sizeof(double) * nc * nc, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    if (chol_upper(nc, G.data(), U1.data())) {
+      CK(cudaMemcpyAsync(Gdev, U1.data(), sizeof(double) * nc * nc, cudaMemcpyHostToDevice, e->st));
+      launch_trsolve(e, nc, e->R, Gdev);
+      have_u1 = true;
+      launch_gram(e, nc, e->R, Gdev);
+      CK(cudaMemcpyAsync(G.data(), Gdev, sizeof(double) * nc * nc, cudaMemcpyDeviceToHost, e->st));
+      CK(cudaStreamSynchronize(e->st));
+      if (chol_upper(nc, G.data(), U2.data())) {
+        // U = U2 U1
+        for (int j = 0; j < nc; j++)
+          for (int i = 0; i <= j; i++) {
+            double t = 0.0;
+            for (int k = i; k <= j; k++) t += U2[(size_t)k * nc + i] * U1[(size_t)j * nc + k];
+            u_aug[(size_t)j * nc + i] = t;
+          }
+        for (int j = 0; j < nc; j++) for (int i = j + 1; i < nc; i++) u_aug[(size_t)j * nc + i] = 0.0;
+        return 0;
+      }
+    }
+  }
+  RC(local_qr_cgs2(e, nc, U));
+  if (have_u1) {
+    // the columns in place were C U1^{-1}: overall factor = U_cgs2 U1
+    for (int j = 0; j < nc; j++)
+      for (int i = 0; i < nc; i++) {
+        double t = 0.0;
+        for (int k = i; k <= j; k++) t += U[(size_t)k * nc + i] * U1[(size_t)j * nc + k];
+        u_aug[(size_t)j * nc + i] = (i <= j) ? t : 0.0;
+      }
+  } else {
+    memcpy(u_aug, U.data(), sizeof(double) * (size_t)nc * nc);
+  }
+  return 0;
+}
+
+static int op_apply_alpha(msp_engine *e, int kind, int s, const double *alpha_host) {
+  memcpy(e->hsc + 216, alpha_host, sizeof(double) * s);
+  CK(cudaMemcpyAsync(e->dsc + 216, e->hsc + 216, sizeof(double) * s, cudaMemcpyHostToDevice, e->st));
+  k_lincomb<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, s, e->ld, e->S, e->dsc + 216, e->x);
+  e->launches++;
+  if (!kind_is_local(kind)) {
+    // the block's copies of the neighbours' boundaries follow x_min = S alpha too (…-semi-local.c:335-338)
+    for (int side = 0; side < 2; side++)
+      if (e->has_nb[side]) {
+        k_lincomb<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->H, s, e->H, side ? e->Shi : e->Slo, e->dsc + 216, e->halo[side]);
+        e->launches++;
+      }
+  }
+  return 0;
+}
+
+static int allreduce_host(msp_engine *e, int first, int n);
+
+// KSPSolve_LSQR (PETSc lsqr.c) on the dense column block R_K (n_K x s) distributed over the blocks:
+// R v and the vector updates are block-local kernels (K10 lincomb, K4 axpy+norm), R^T u is the MDot kernel (K3);
+// with `global` the s-vector R^T u and the two norms of every iteration are summed over blocks (the reference's
+// MatMultTranspose_MPIDense / VecNorm_MPI allreduces).  Zero initial guess, initial-residual-norm test
+// (outer_solver_norm_equation utils.c:1065-1068); returns alpha, phibar and the iteration count.
+static int op_lsqr(msp_engine *e, int kind, int s, bool global, int max_it, double rtol, double abstol, double *alpha, double *rnorm_out,
+                   int *its_out) {
+  const double *rhs_src = kind_is_local(kind) ? e->rhs : e->b;
+  double *U = e->Wb[0], *U1 = e->Wb[1];
+  std::vector<double> V(s, 0.0), V1(s, 0.0), W(s, 0.0);
+  auto sum_blocks = [&](int first, int n) -> int { return global ? allreduce_host(e, first, n) : read_scalars(e, first, n); };
+  auto put_s = [&](const std::vector<double> &v) -> int {
+    memcpy(e->hsc + 216, v.data(), sizeof(double) * s);
+    CK(cudaMemcpyAsync(e->dsc + 216, e->hsc + 216, sizeof(double) * s, cudaMemcpyHostToDevice, e->st));
+    return 0;
+  };
+  for (int j = 0; j < s; j++) alpha[j] = 0.0;
+  k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, rhs_src, U);
+  k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, U, 0.0, e->ws, 2, e->dsc + 4);
+  e->launches += 2;
+  RC(sum_blocks(4, 1));
+  double rnorm = std::sqrt(e->hsc[4]);
+  const double rnorm0 = rnorm, ttol = std::max(rtol * rnorm0, abstol);
+  int its = 0;
+  if (rnorm > 0.0) {
+    double beta = rnorm, al;
+    k_scale<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, 1.0 / beta, U);
+    e->launches++;
+    launch_mdot(e, s, e->R, e->ld, U, e->dsc + 64, 1.0, -1, 0);
+    RC(sum_blocks(64, s));
+    double nv = 0.0;
+    for (int j = 0; j < s; j++) { V[j] = e->hsc[64 + j]; nv += V[j] * V[j]; }
+    al = std::sqrt(nv);
+    if (al > 0.0) for (int j = 0; j < s; j++) V[j] /= al;
+    W = V;
+    double phibar = beta, rhobar = al;
+    int i = 0;
+    do {
+      RC(put_s(V));
+      k_lincomb<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, s, e->ld, e->R, e->dsc + 216, U1); // U1 = R V
+      e->launches++;
+      e->hsc[5] = -al;
+      CK(cudaMemcpyAsync(e->dsc + 5, e->hsc + 5, sizeof(double), cudaMemcpyHostToDevice, e->st));
+      launch_maxpy<0>(e, 1, U, e->ld, e->dsc + 5, U1, e->dsc + 6, -1, 0, 0, 3); // U1 -= alpha U, ||U1||
+      RC(read_scalars(e, 6, 1));
+      e->hsc[6] = e->hsc[6] * e->hsc[6];
+      CK(cudaMemcpyAsync(e->dsc + 6, e->hsc + 6, sizeof(double), cudaMemcpyHostToDevice, e->st));
+      RC(sum_blocks(6, 1));
+      beta = std::sqrt(e->hsc[6]);
+      if (beta > 0.0) { k_scale<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, 1.0 / beta, U1); e->launches++; }
+      launch_mdot(e, s, e->R, e->ld, U1, e->dsc + 64, 1.0, -1, 0); // V1 = R^T U1
+      RC(sum_blocks(64, s));
+      nv = 0.0;
+      for (int j = 0; j < s; j++) { V1[j] = std::fma(-beta, V[j], e->hsc[64 + j]); nv += V1[j] * V1[j]; }
+      al = std::sqrt(nv);
+      if (al > 0.0) for (int j = 0; j < s; j++) V1[j] /= al;
+      const double rho = std::sqrt(rhobar * rhobar + beta * beta);
+      const double c = rhobar / rho, sn = beta / rho, theta = sn * al;
+      rhobar = -c * al;
+      const double phi = c * phibar;
+      phibar = sn * phibar;
+      for (int j = 0; j < s; j++) alpha[j] = std::fma(phi / rho, W[j], alpha[j]);
+      for (int j = 0; j < s; j++) W[j] = V1[j] + (-theta / rho) * W[j];
+      rnorm = phibar;
+      its++;
+      // KSPConvergedDefault with -ksp_convergence_test default (running_bulk_test_g5k:247)
+      bool conv = std::isnan(rnorm) || std::isinf(rnorm) || rnorm <= ttol || rnorm >= 1e4 * rnorm0;
+      if (conv) break;
+      std::swap(U, U1);
+      std::swap(V, V1);
+      i++;
+    } while (i < max_it);
+  }
+  if (rnorm_out) *rnorm_out = rnorm;
+  if (its_out) *its_out = its;
+  return 0;
+}
+
+// Normal-equations minimiser (the reference's `outer_solver`, utils.c:972-996: MatTransposeMatMult(R,R), MatMultTranspose(R,b),
+// KSPSolve on the s x s system): ONE Gram pass over [R_K | rhs] (K9), one allreduce of the (s+1)^2 Gram entries when the
+// least squares is global ("NCCL Gram allreduce"), Cholesky on the host.  Squares the condition number: offered for
+// completeness, TSQR stays the default.  ||b - R alpha|| from a second pass (not from b'b - g'alpha: cancellation).
+static int op_normal_equations(msp_engine *e, int kind, int s, bool global, double *alpha, double *rnorm_out) {
+  const int nc = s + 1;
+  if (nc > 9) MSP_FAIL("the normal-equations minimiser supports s <= 8");
+  const double *rhs_src = kind_is_local(kind) ? e->rhs : e->b;
+  double *bcol = e->R + (long long)s * e->ld;
+  k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, rhs_src, bcol);
+  e->launches++;
+  launch_gram(e, nc, e->R, e->dfac);
+  if (global) RC(e->comm->allreduce_sum(e->dfac, nc * nc, e->st));
+  std::vector<double> G((size_t)nc * nc), U((size_t)s * s), Gs((size_t)s * s);
+  CK(cudaMemcpyAsync(G.data(), e->dfac, sizeof(double) * nc * nc, cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  for (int j = 0; j < s; j++) for (int i = 0; i <= j; i++) Gs[(size_t)j * s + i] = G[(size_t)j * nc + i];
+  if (!chol_upper(s, Gs.data(), U.data())) MSP_FAIL("normal equations: the Gram matrix is not positive definite at working precision (use the TSQR minimiser)");
+  // U^T U alpha = g, g = R^T b = last column of the augmented Gram
+  std::vector<double> y(s);
+  for (int i = 0; i < s; i++) {
+    double t = G[(size_t)s * nc + i];
+    for (int k = 0; k < i; k++) t -= U[(size_t)i * s + k] * y[k];
+    y[i] = t / U[(size_t)i * s + i];
+  }
+  for (int i = s - 1; i >= 0; i--) {
+    double t = y[i];
+    for (int k = i + 1; k < s; k++) t -= U[(size_t)k * s + i] * alpha[k];
+    alpha[i] = t / U[(size_t)i * s + i];
+  }
+  if (rnorm_out) {
+    // r = rhs - R alpha, in place in the rhs column
+    for (int j = 0; j < s; j++) e->hsc[216 + j] = -alpha[j];
+    CK(cudaMemcpyAsync(e->dsc + 216, e->hsc + 216, sizeof(double) * s, cudaMemcpyHostToDevice, e->st));
+    launch_maxpy<0>(e, s, e->R, e->ld, e->dsc + 216, bcol, e->dsc + 6, -1, 0, 0, 3);
+    RC(read_scalars(e, 6, 1));
+    e->hsc[6] = e->hsc[6] * e->hsc[6];
+    if (global) {
+      CK(cudaMemcpyAsync(e->dsc + 6, e->hsc + 6, sizeof(double), cudaMemcpyHostToDevice, e->st));
+      RC(allreduce_host(e, 6, 1));
+    }
+    *rnorm_out = std::sqrt(e->hsc[6]);
+  }
+  return 0;
+}
+
+// small dense least squares on the host: stack nfac upper factors [U_k | c_k; 0 rho_k] and solve by
+// Householder QR.  This is the root of the TSQR tree (s <= 32: a few kflop).
+static int tsqr_combine(int s, int nfac, const double *uall, double *alpha, double *resnorm) {
+  const int nc = s + 1, rows = nfac * nc;
+  std::vector<double> A((size_t)rows * nc, 0.0); // column-major rows x nc
+  for (int f = 0; f < nfac; f++)
+    for (int c = 0; c < nc; c++)
+      for (int r = 0; r <= c; r++) A[(size_t)c * rows + f * nc + r] = uall[(size_t)f * nc * nc + (size_t)c * nc + r];
+  std::vector<double> diag(nc, 0.0);
+  for (int k = 0; k < nc; k++) {
+    double *a = &A[(size_t)k * rows];
+    double nrm = 0.0;
+    for (int r = k; r < rows; r++) nrm += a[r] * a[r];
+    nrm = std::sqrt(nrm);
+    if (nrm == 0.0) { diag[k] = 0.0; continue; }
+    double beta = (a[k] >= 0.0) ? -nrm : nrm;
+    a[k] -= beta;
+    double vtv = 0.0;
+    for (int r = k; r < rows; r++) vtv += a[r] * a[r];
+    for (int j = k + 1; j < nc; j++) {
+      double *aj = &A[(size_t)j * rows];
+      double d = 0.0;
+      for (int r = k; r < rows; r++) d += a[r] * aj[r];
+      d = 2.0 * d / vtv;
+      for (int r = k; r < rows; r++) aj[r] -= d * a[r];
+    }
+    diag[k] = beta;
+  }
+  // back substitution on the leading s x s block against column s
+  const double *cvec = &A[(size_t)s * rows];
+  double dmax = 0.0;
+  for (int k = 0; k < s; k++) dmax = std::max(dmax, std::fabs(diag[k]));
+  for (int k = s - 1; k >= 0; k--) {
+    double t = cvec[k];
+    for (int j = k + 1; j < s; j++) t -= A[(size_t)j * rows + k] * alpha[j];
+    // numerically dependent basis vector (iterates identical to rounding): drop it
+    alpha[k] = (std::fabs(diag[k]) > 1e-14 * dmax) ? t / diag[k] : 0.0;
+  }
+  if (resnorm) *resnorm = std::fabs(diag[s]);
+  return 0;
+}
+
