@@ -111,3 +111,13 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["higher_is_better"] is False and line["vs_baseline"] is None
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"] and line["dtype"] == "f64"
+
+
+def test_bench_gpu_arm_refuses_to_run_without_gpu():
+    """No CPU fallback: on a box without CUDA the product arm of bench.py exits non-zero and says so."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)

@@ -325,6 +325,20 @@ def test_async_scheduled_matches_oracle(S, oracle, alg, s):
     grp.close()
 
 
+def test_async_scheduled_four_blocks_and_3d(S, oracle):
+    """Chain of four block roots with uneven speeds (2-D), and a 3-D problem: same steps per block as the oracle."""
+    inner = dict(restart=30, max_it=3, rtol=1e-10, abstol=1e-100)
+    for alg, dims, s, periods in (("AM", (32, 16, 1), 0, [1, 2, 1, 3]), ("AMAM_GLOBAL", (8, 8, 8), 3, [2, 1, 1, 1])):
+        m, n, p = dims
+        ref = oracle.solve(alg, m, n, p=p, nblocks=4, s=s, rtol=1e-4, inner=inner, periods=periods, max_outer=6000)
+        grp = S.Group(m, n, p, nblocks=4, s=s, max_restart=30)
+        res = grp.solve(alg, s=s, rtol=1e-4, inner=S.ksp_opts(**inner), max_outer=6000, periods=periods)
+        its = [r["outer_its"] for r in res]
+        assert all(abs(a - b) <= max(2, round(0.1 * b)) for a, b in zip(its, ref["outer_its_block"])), (alg, its, ref["outer_its_block"])
+        assert res[0]["final_residual"] <= 1e-3 * res[0]["norm0"]
+        grp.close()
+
+
 @pytest.mark.parametrize("alg,s,G", [("AM", 0, 2), ("AMAM_GLOBAL", 3, 4), ("AMAM_LOCAL", 3, 2)])
 def test_async_free_running_reaches_residual(S, alg, s, G):
     """Barrier-free run (one host thread per block, no schedule): judged on the true residual after the closing

@@ -186,3 +186,13 @@ def test_async_drivers_reach_residual(oracle):
     for alg in ("AMAM_GLOBAL", "AMAM_SEMI_LOCAL", "AMAM_LOCAL"):
         r = oracle.solve(alg, 24, 24, nblocks=2, s=4, rtol=1e-5, inner=inner, periods=[1, 2], max_outer=4000)
         assert r["rc"] == 0 and r["final_residual"] <= 1e-4 * r["norm0"], alg
+
+
+def test_async_four_blocks_chain_terminates(oracle):
+    """Generalisation of the 2-block detector to a chain of block roots: uneven speeds, 4 blocks,
+    2-D and 3-D; every block reaches FINISHED through partial-CV / verification / response / verdict messages."""
+    inner = dict(restart=30, max_it=3, rtol=1e-10, abstol=1e-100)
+    r = oracle.solve("AM", 32, 16, nblocks=4, rtol=1e-4, inner=inner, periods=[1, 2, 1, 3], max_outer=6000)
+    assert r["rc"] == 0 and all(i > 0 for i in r["outer_its_block"]) and r["final_residual"] <= 1e-3 * r["norm0"]
+    r = oracle.solve("AMAM_GLOBAL", 8, 8, p=8, nblocks=4, s=3, rtol=1e-4, inner=inner, periods=[2, 1, 1, 1], max_outer=6000)
+    assert r["rc"] == 0 and r["final_residual"] <= 1e-3 * r["norm0"]
