@@ -61,6 +61,11 @@ int msp_dimension_related(int nprocs, int npb, int rank, int m, int n, int *njac
 int msp_create(const msp_problem *prob, int device, msp_engine **out) { return engine_create(prob, device, out); }
 int msp_destroy(msp_engine *e) { return engine_free(e); }
 int msp_rows(const msp_engine *e) { return e ? e->nb : -1; }
+int msp_spmv_format(const msp_engine *e, int *width) {
+  if (!e) return -1;
+  if (width) *width = e->dval ? e->dia.nd : e->W;
+  return e->dval ? 1 : 0;
+}
 int msp_halo_size(const msp_engine *e) { return e ? e->H : -1; }
 
 static int sub_extract(msp_engine *e, int which, int32_t *orp_h, int32_t *oci_h, double *ova_h, int64_t *nnz_out) {

@@ -83,6 +83,7 @@ struct msp_engine {
   int64_t nnz = 0;
   int *rp = nullptr, *ci = nullptr; double *va = nullptr; // strip CSR
   int *ecol = nullptr; double *eval = nullptr;            // ELL
+  double *dval = nullptr; DiaOffsets dia{};               // DIA view (hot SpMV) when the strip has <= 8 diagonals
   int *brow = nullptr; int nbrow = 0;
   double *b = nullptr, *rhs = nullptr, *x = nullptr;
   double *halo[2] = {nullptr, nullptr}; // private copies of the neighbours' boundary layers
@@ -230,7 +231,18 @@ template <int MODE, bool RESID, bool SCALE, bool NORM>
 static void launch_spmv_w(msp_engine *e, const SpmvArgs &a, int ws_slot, GmresCtl *ctl_rw) {
   const long long items = ((long long)a.nb + 1) / 2;
   e->prof_begin(0, 12.0 * (double)e->nnz + 4.0 * (e->nb + 1) + 16.0 * e->nb + (RESID ? 8.0 * e->nb : 0.0));
-  if (a.W == 5) {
+  if (a.dval) {
+    if (a.dia.nd == 5) {
+      auto k = k_spmv_dia<5, MODE, RESID, SCALE, NORM>;
+      k<<<grid_for(items, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
+    } else if (a.dia.nd == 7) {
+      auto k = k_spmv_dia<7, MODE, RESID, SCALE, NORM>;
+      k<<<grid_for(items, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
+    } else {
+      auto k = k_spmv_dia<0, MODE, RESID, SCALE, NORM>;
+      k<<<grid_for(items, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
+    }
+  } else if (a.W == 5) {
     auto k = k_spmv_ell<5, MODE, RESID, SCALE, NORM>;
     k<<<grid_for(items, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
   } else if (a.W == 7) {
@@ -247,6 +259,7 @@ static void launch_spmv_w(msp_engine *e, const SpmvArgs &a, int ws_slot, GmresCt
 static SpmvArgs spmv_args(msp_engine *e, const double *x, double *y) {
   SpmvArgs a{};
   a.nb = e->nb; a.W = e->W; a.H = e->H; a.ld = e->ld; a.ecol = e->ecol; a.eval = e->eval;
+  a.dval = e->dval; a.dia = e->dia;
   a.x = x; a.y = y; a.lo = nullptr; a.hi = nullptr; a.b = nullptr; a.ctl = e->ctl; a.guard_it = -1;
   return a;
 }
@@ -297,7 +310,7 @@ static int engine_free(msp_engine *e) {
   for (auto &kv : e->cycle_graphs) cudaGraphExecDestroy(kv.second.exec);
   for (int J = 0; J < MSP_MAX_BLOCKS; J++)
     if (e->peer_any[J].base && e->peer_any_ipc[J]) cudaIpcCloseMemHandle(e->peer_any[J].base);
-  void *ptrs[] = {e->rp, e->ci, e->va, e->ecol, e->eval, e->brow, e->b, e->rhs, e->x, e->halo[0], e->halo[1], e->V, e->Wb[0],
+  void *ptrs[] = {e->rp, e->ci, e->va, e->ecol, e->eval, e->dval, e->brow, e->b, e->rhs, e->x, e->halo[0], e->halo[1], e->V, e->Wb[0],
                   e->Wb[1], e->S, e->Slo, e->Shi, e->R, e->ctl, e->ws.partial, e->ws.counter, e->dsc, e->dfac, e->gram_partial, e->win.base, e->cd, e->aint, e->dec};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (e->hsc) cudaFreeHost(e->hsc);
@@ -362,6 +375,34 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
     if (e->nbrow) {
       if (cudaMalloc(&e->brow, sizeof(int) * rows.size()) != cudaSuccess) { g_err = "oom"; return fail(1); }
       cudaMemcpy(e->brow, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice);
+    }
+  }
+  // ---- DIA view: which diagonals occur?  (decided from the assembled CSR; ELL stays the general fallback)
+  if (getenv("MSPLIT_NO_DIA") == nullptr) {
+    const size_t words = ((size_t)2 * e->H + 1 + 31) / 32;
+    unsigned *bitmap = nullptr; int *oor = nullptr;
+    if (cudaMalloc(&bitmap, sizeof(unsigned) * words) != cudaSuccess || cudaMalloc(&oor, sizeof(int)) != cudaSuccess) { g_err = "oom"; return fail(1); }
+    cudaMemsetAsync(bitmap, 0, sizeof(unsigned) * words, e->st);
+    cudaMemsetAsync(oor, 0, sizeof(int), e->st);
+    k_mark_offsets<<<grid_for(e->nb, 16), MSPK_THREADS, 0, e->st>>>(e->nb, e->off, e->H, e->rp, e->ci, bitmap, oor);
+    std::vector<unsigned> hb(words);
+    int hoor = 0;
+    cudaMemcpyAsync(hb.data(), bitmap, sizeof(unsigned) * words, cudaMemcpyDeviceToHost, e->st);
+    cudaMemcpyAsync(&hoor, oor, sizeof(int), cudaMemcpyDeviceToHost, e->st);
+    cudaStreamSynchronize(e->st);
+    cudaFree(bitmap); cudaFree(oor);
+    std::vector<int> offs;
+    for (size_t w = 0; w < words && offs.size() <= 8; w++)
+      for (int b = 0; b < 32 && hb[w]; b++)
+        if (hb[w] & (1u << b)) { offs.push_back((int)(w * 32 + b) - e->H); if (offs.size() > 8) break; }
+    if (!hoor && !offs.empty() && offs.size() <= 8) {
+      e->dia.nd = (int)offs.size();
+      for (int j = 0; j < e->dia.nd; j++) e->dia.off[j] = offs[j]; // ascending = sorted-column order of every row
+      const size_t bytes = sizeof(double) * (size_t)e->ld * e->dia.nd;
+      if (cudaMalloc(&e->dval, bytes) != cudaSuccess) { g_err = "out of device memory (DIA)"; return fail(1); }
+      cudaMemsetAsync(e->dval, 0, bytes, e->st);
+      k_csr_to_dia<<<grid_for(e->nb, 16), MSPK_THREADS, 0, e->st>>>(e->nb, e->ld, e->off, e->rp, e->ci, e->va, e->dia, e->dval);
+      cudaStreamSynchronize(e->st);
     }
   }
   if (!p->keep_csr) {

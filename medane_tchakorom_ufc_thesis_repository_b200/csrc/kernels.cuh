@@ -266,6 +266,34 @@ __global__ void k_mark_boundary(int nb, int W, long long ld, const int *__restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// Diagonal (DIA) view of a strip whose entries sit on at most 8 distinct diagonals (col - row), which is what the
+// 5-/7-point stencil strips are.  Found by inspecting the assembled CSR, not assumed: k_mark_offsets sets one bit per
+// occurring offset, the host sorts them ascending (= sorted-column order of every row), k_csr_to_dia scatters the
+// values into ND slot-major arrays (missing entries 0).  The hot SpMV then needs NO index loads: 8 ND + 16 bytes per
+// row instead of 12 W + 16.  fma(0, x, s) == s keeps the result bit-identical to the CSR chain.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_mark_offsets(int nb, int off, int H, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                               unsigned int *bitmap /* 2H+1 bits */, int *out_of_range) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nb; r += (long long)gridDim.x * blockDim.x)
+    for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
+      const long long d = (long long)colidx[k] - (off + r);
+      if (d < -H || d > H) { *out_of_range = 1; continue; }
+      const unsigned bit = (unsigned)(d + H);
+      atomicOr(bitmap + (bit >> 5), 1u << (bit & 31));
+    }
+}
+struct DiaOffsets { int nd; int off[8]; };
+__global__ void k_csr_to_dia(int nb, long long ld, int off, const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                             const double *__restrict__ val, DiaOffsets d, double *__restrict__ dval /* zero-initialised */) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nb; r += (long long)gridDim.x * blockDim.x)
+    for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
+      const int dd = colidx[k] - (off + (int)r);
+      for (int j = 0; j < d.nd; j++)
+        if (d.off[j] == dd) { dval[j * ld + r] = val[k]; break; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1/K2  ELL SpMV  y = A x | y = b - A x,  optional deferred normalisation of the input
 // (v = w * inv written to vout, K5) and optional fused ||y||^2 (cycle prologue).
 // Two rows per thread: 128-bit loads of the values, 64-bit of the indices, all coalesced
@@ -277,6 +305,8 @@ struct SpmvArgs {
   long long ld;
   const int *ecol;
   const double *eval;
+  const double *dval;   // DIA values (slot-major), or null
+  DiaOffsets dia;
   const double *x;      // input (own rows)
   const double *lo, *hi; // neighbour boundaries (MODE 1), may be null
   const double *b;      // RESID: y = b - A x
@@ -348,6 +378,65 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_spmv_ell(SpmvArgs a, ReduceWs 
       if (threadIdx.x == 0) {
         ws.counter[ws_slot] = 0;
         ws.partial[ws_slot * MSPK_MAX_PART + MSPK_MAX_PART - 1] = tot; // also left readable for the host
+        if (ctl_rw) ctl_cycle_begin(ctl_rw, sqrt(tot));
+      }
+    }
+  }
+}
+
+// DIA SpMV: same contract, template flags and epilogue as k_spmv_ell; columns are r + off[k], no index stream.
+template <int ND_T, int MODE, bool RESID, bool SCALE, bool NORM>
+__global__ void __launch_bounds__(MSPK_THREADS) k_spmv_dia(SpmvArgs a, ReduceWs ws, int ws_slot, GmresCtl *ctl_rw) {
+  if (a.guard_it >= 0) {
+    if (!a.ctl->active || a.ctl->it != a.guard_it) return;
+  }
+  const int ND = (ND_T > 0) ? ND_T : a.dia.nd;
+  const double inv = SCALE ? a.ctl->inv_arr[a.guard_it > 0 ? a.guard_it : 0] : 1.0;
+  double nrm = 0.0;
+  const long long npairs = (a.nb + 1) >> 1;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npairs; p += (long long)gridDim.x * blockDim.x) {
+    const long long r = p * 2;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < ((ND_T > 0) ? ND_T : 8); k++) {
+      if (ND_T == 0 && k >= ND) break;
+      const double2 v = ld_stream2(a.dval + k * a.ld + r);
+      const int c = (int)r + a.dia.off[k];
+      const double x0 = gather_x<MODE>(a, c, inv, SCALE);
+      const double x1 = gather_x<MODE>(a, c + 1, inv, SCALE);
+      s0 = fma(v.x, x0, s0);
+      s1 = fma(v.y, x1, s1);
+    }
+    if (RESID) {
+      s0 = a.b[r] - s0;
+      if (r + 1 < a.nb) s1 = a.b[r + 1] - s1;
+    }
+    if (r + 1 < a.nb) {
+      *reinterpret_cast<double2 *>(a.y + r) = make_double2(s0, s1);
+      if (NORM) nrm = fma(s0, s0, fma(s1, s1, nrm));
+    } else {
+      a.y[r] = s0;
+      if (NORM) nrm = fma(s0, s0, nrm);
+    }
+  }
+  if (NORM) {
+    __shared__ double sm[32];
+    __shared__ bool last;
+    double bs = block_sum(nrm, sm);
+    if (threadIdx.x == 0) {
+      ws.partial[ws_slot * MSPK_MAX_PART + blockIdx.x] = bs;
+      __threadfence();
+      unsigned t = atomicAdd(ws.counter + ws_slot, 1u);
+      last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+      double v = 0.0;
+      for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += __ldcg(ws.partial + ws_slot * MSPK_MAX_PART + i);
+      double tot = block_sum(v, sm);
+      if (threadIdx.x == 0) {
+        ws.counter[ws_slot] = 0;
+        ws.partial[ws_slot * MSPK_MAX_PART + MSPK_MAX_PART - 1] = tot;
         if (ctl_rw) ctl_cycle_begin(ctl_rw, sqrt(tot));
       }
     }

@@ -86,6 +86,12 @@ class Engine:
         self.nb = _lib.lib().msp_rows(self.h)
         self.H = _lib.lib().msp_halo_size(self.h)
 
+    def spmv_format(self):
+        """("dia" | "ell", width) of the storage the hot SpMV reads."""
+        w = C.c_int()
+        kind = _lib.lib().msp_spmv_format(self.h, C.byref(w))
+        return ("dia" if kind == 1 else "ell"), w.value
+
     def close(self):
         if self._owner is None and getattr(self, "h", None):
             _lib.lib().msp_destroy(self.h)

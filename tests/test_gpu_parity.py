@@ -140,6 +140,28 @@ def test_mdot_maxpy(S, nv):
     e.close()
 
 
+def test_dia_view_detected_and_identical_to_ell(S, oracle, monkeypatch):
+    """The hot SpMV streams a DIA view when the strip has <= 8 diagonals (5 / 7 for the Poisson strips); forcing the ELL
+    path (MSPLIT_NO_DIA) gives bit-identical products."""
+    rng = np.random.default_rng(9)
+    for dims, G, K, nd in (((48, 40, 1), 3, 1, 5), ((10, 9, 8), 2, 1, 7)):
+        m, n, p = dims
+        e = S.Engine(m, n, p, block=K, nblocks=G)
+        assert e.spmv_format() == ("dia", nd)
+        nb, H = e.nb, e.H
+        x = rng.standard_normal(nb); lo = rng.standard_normal(H); hi = rng.standard_normal(H)
+        y_dia = e.spmv(S.MAT_STRIP, x, lo, hi if K < G - 1 else None)
+        yd_dia = e.spmv(S.MAT_DIAG, x)
+        e.close()
+        monkeypatch.setenv("MSPLIT_NO_DIA", "1")
+        e = S.Engine(m, n, p, block=K, nblocks=G)
+        assert e.spmv_format()[0] == "ell"
+        assert np.array_equal(y_dia, e.spmv(S.MAT_STRIP, x, lo, hi if K < G - 1 else None))
+        assert np.array_equal(yd_dia, e.spmv(S.MAT_DIAG, x))
+        e.close()
+        monkeypatch.delenv("MSPLIT_NO_DIA")
+
+
 def test_update_rhs_and_residuals(S, oracle):
     rng = np.random.default_rng(5)
     m, n, G, K = 30, 20, 3, 1

@@ -33,7 +33,10 @@ def rec(name, ms, bytes_):
 
 
 rec("copy (STREAM)", e.bench_kernel(4, iters=20), 16 * n)
-rec("spmv ELL  [CSR bytes]", e.bench_kernel(0, iters=20), 12 * nnz + 4 * (n + 1) + 16 * n)
+fmt, width = e.spmv_format()
+ms = e.bench_kernel(0, iters=20)
+rec(f"spmv {fmt.upper()} [CSR bytes]", ms, 12 * nnz + 4 * (n + 1) + 16 * n)
+rec(f"spmv {fmt.upper()} [own {width}-wide bytes]", ms, ((8 if fmt == "dia" else 12) * width + 16) * n)
 ms = e.bench_kernel(5, iters=20)
 rec("spmv, input scaled on the fly", ms, 12 * nnz + 4 * (n + 1) + 16 * n)
 for nv in (1, 2, 4, 8, 9, 16, 24, 30):
