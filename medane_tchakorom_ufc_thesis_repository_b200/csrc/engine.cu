@@ -150,7 +150,6 @@ struct msp_engine {
   struct CycleGraph { cudaGraphExec_t exec; int launches; };
   std::map<CycleKey, CycleGraph> cycle_graphs;
   bool use_graphs = true;
-  bool snake = true; // MAXPY walks the rows backwards (L2 reuse of what MDot read last)
   // deterministic turn taking for the emulated asynchronous schedule
   struct msp_group *grp = nullptr;
 };
@@ -294,7 +293,7 @@ static void launch_maxpy(msp_engine *e, int nv, const double *V, long long ldv, 
                          int guard_it, int guard_refine, int pass, int ws_slot, const double *inv = nullptr) {
   MaxpyArgs a{};
   a.nb = e->nb; a.nv = nv; a.ld = ldv; a.V = V; a.coef = coef; a.w = w; a.norm_out = norm_out; a.ctl = e->ctl; a.inv = inv;
-  a.guard_it = guard_it; a.guard_refine = guard_refine; a.pass = pass; a.reverse = e->snake ? 1 : 0;
+  a.guard_it = guard_it; a.guard_refine = guard_refine; a.pass = pass;
   e->prof_begin(2, 8.0 * e->nb * (nv + 2));
   k_maxpy_norm<FIN><<<grid_for((long long)e->nb / 4, 8), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot);
   e->prof_end();
@@ -446,7 +445,6 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   if (!ok) { g_err = "out of device memory (vectors)"; return fail(1); }
   e->comm = new SelfComm(); e->own_comm = true;
   e->use_graphs = getenv("MSPLIT_NO_GRAPHS") == nullptr;
-  e->snake = getenv("MSPLIT_NO_SNAKE") == nullptr;
   // ---- b_K = A_K,: * 1 (computeTheRightHandSideWithInitialGuess utils.c:626): halos of ones ----
   {
     k_fill<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, 1.0, e->Wb[0]);

@@ -558,7 +558,6 @@ struct MaxpyArgs {
   GmresCtl *ctl;
   int guard_it, guard_refine;
   int pass;            // CGS pass index (0 or 1)
-  int reverse;         // traverse the rows from the end: MDot ran front to back, so the tail of V is what L2 still holds
 };
 
 template <int FIN>
@@ -577,16 +576,15 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
   long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   // two row-pairs per thread per trip, 8 basis vectors per chunk: 16 independent 16-byte loads in flight
   for (; p + stride < npairs; p += 2 * stride) {
-    const long long q0 = a.reverse ? npairs - 1 - p : p, q1 = a.reverse ? npairs - 1 - (p + stride) : p + stride;
-    double2 t0 = __ldcs(reinterpret_cast<const double2 *>(a.w + 2 * q0));
-    double2 t1 = __ldcs(reinterpret_cast<const double2 *>(a.w + 2 * q1));
+    double2 t0 = __ldcs(reinterpret_cast<const double2 *>(a.w + 2 * p));
+    double2 t1 = __ldcs(reinterpret_cast<const double2 *>(a.w + 2 * (p + stride)));
     int j = 0;
     for (; j + 8 <= a.nv; j += 8) {
       double2 x0[8], x1[8];
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        x0[u] = ld_stream2(a.V + (long long)(j + u) * a.ld + 2 * q0);
-        x1[u] = ld_stream2(a.V + (long long)(j + u) * a.ld + 2 * q1);
+        x0[u] = ld_stream2(a.V + (long long)(j + u) * a.ld + 2 * p);
+        x1[u] = ld_stream2(a.V + (long long)(j + u) * a.ld + 2 * (p + stride));
       }
 #pragma unroll
       for (int u = 0; u < 8; u++) {
@@ -600,8 +598,8 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
 #pragma unroll
       for (int u = 0; u < 8; u++)
         if (j + u < a.nv) {
-          x0[u] = ld_stream2(a.V + (long long)(j + u) * a.ld + 2 * q0);
-          x1[u] = ld_stream2(a.V + (long long)(j + u) * a.ld + 2 * q1);
+          x0[u] = ld_stream2(a.V + (long long)(j + u) * a.ld + 2 * p);
+          x1[u] = ld_stream2(a.V + (long long)(j + u) * a.ld + 2 * (p + stride));
         }
 #pragma unroll
       for (int u = 0; u < 8; u++)
@@ -611,19 +609,18 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
           t1.x = fma(c, x1[u].x, t1.x); t1.y = fma(c, x1[u].y, t1.y);
         }
     }
-    __stcs(reinterpret_cast<double2 *>(a.w + 2 * q0), t0);
-    __stcs(reinterpret_cast<double2 *>(a.w + 2 * q1), t1);
+    __stcs(reinterpret_cast<double2 *>(a.w + 2 * p), t0);
+    __stcs(reinterpret_cast<double2 *>(a.w + 2 * (p + stride)), t1);
     nrm = fma(t0.x, t0.x, fma(t0.y, t0.y, nrm));
     nrm = fma(t1.x, t1.x, fma(t1.y, t1.y, nrm));
   }
   for (; p < npairs; p += stride) {
-    const long long q = a.reverse ? npairs - 1 - p : p;
-    double2 t = *reinterpret_cast<const double2 *>(a.w + 2 * q);
+    double2 t = *reinterpret_cast<const double2 *>(a.w + 2 * p);
     for (int j = 0; j < a.nv; j++) {
-      const double2 x = ld_stream2(a.V + (long long)j * a.ld + 2 * q);
+      const double2 x = ld_stream2(a.V + (long long)j * a.ld + 2 * p);
       t.x = fma(cf[j], x.x, t.x); t.y = fma(cf[j], x.y, t.y);
     }
-    *reinterpret_cast<double2 *>(a.w + 2 * q) = t;
+    *reinterpret_cast<double2 *>(a.w + 2 * p) = t;
     nrm = fma(t.x, t.x, fma(t.y, t.y, nrm));
   }
   if ((a.nb & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
