@@ -274,9 +274,17 @@ __global__ void k_mark_boundary(int nb, int W, long long ld, const int *__restri
 // ------------------------------------------------------------------------------------------------
 __global__ void k_mark_offsets(int nb, int off, int H, const int *__restrict__ rowptr, const int *__restrict__ colidx,
                                unsigned int *bitmap /* 2H+1 bits */, int *out_of_range) {
+  // every thread remembers the offsets it has already published (a stencil strip has 5 or 7 in total), so the
+  // bitmap sees a handful of atomics per thread instead of one per non-zero
+  long long seen[8];
+  int nseen = 0;
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < nb; r += (long long)gridDim.x * blockDim.x)
     for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
       const long long d = (long long)colidx[k] - (off + r);
+      bool known = false;
+      for (int j = 0; j < nseen; j++) known |= (seen[j] == d);
+      if (known) continue;
+      if (nseen < 8) seen[nseen++] = d;
       if (d < -H || d > H) { *out_of_range = 1; continue; }
       const unsigned bit = (unsigned)(d + H);
       atomicOr(bitmap + (bit >> 5), 1u << (bit & 31));
