@@ -201,11 +201,11 @@ def run_gpu(args):
         roof[c] = {"ms": ms, "launches": prof[c]["launches"], "GBps": (prof[c]["bytes"] / (ms * 1e-3) / 1e9) if ms > 0 else 0.0}
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # the SpMV class is accounted with the CSR formula of SURVEY §8(d) (12 nnz + 4 (n+1) + 16 n); the bytes of the storage
-    # the kernel really streams (DIA: values only; ELL: values + indices) are reported beside it
+    # the kernel really streams (coded DIA: one presence byte per row; DIA: values only; ELL: values + indices) are reported beside it
     fmt, width = eng.spmv_format()
     cfg = workload_config(args, world)
     csr_per_row = 12.0 * cfg["nnz"] / cfg["rows"] + 20.0
-    own_per_row = (8.0 if fmt == "dia" else 12.0) * width + 16.0
+    own_per_row = type(eng).spmv_bytes_per_row(fmt, width)
     roof["spmv"]["own"] = {"format": fmt, "width": width, "bytes_per_row": own_per_row,
                            "GBps": roof["spmv"]["GBps"] * own_per_row / csr_per_row,
                            "frac": roof["spmv"]["GBps"] * own_per_row / csr_per_row / peak}

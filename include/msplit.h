@@ -140,8 +140,10 @@ int msp_create(const msp_problem *prob, int device, msp_engine **out);
 int msp_destroy(msp_engine *e);
 int msp_rows(const msp_engine *e);      /* jacobi_block_size */
 int msp_halo_size(const msp_engine *e); /* one grid line (2-D) / plane (3-D) */
-/* storage the hot SpMV reads: returns 1 = DIA (strip with <= 8 diagonals: values only, 8*width + 16 bytes per row),
- * 0 = slot-major ELL (values + indices, 12*width + 16 bytes per row); *width = diagonals / slots */
+/* storage the hot SpMV reads: returns 2 = coded DIA (<= 8 diagonals, each one constant wherever present: one presence
+ * byte per row, 1 + 16 bytes per row), 1 = DIA (<= 8 diagonals: values only, 8*width + 16 bytes per row),
+ * 0 = slot-major ELL (values + indices, 12*width + 16 bytes per row); *width = diagonals / slots.
+ * Environment: MSPLIT_NO_CDIA=1 keeps the plain DIA view, MSPLIT_NO_DIA=1 the ELL view. */
 int msp_spmv_format(const msp_engine *e, int *width);
 int64_t msp_mat_nnz(msp_engine *e, int which);
 int msp_get_csr(msp_engine *e, int which, int32_t *rowptr, int32_t *colidx, double *val);

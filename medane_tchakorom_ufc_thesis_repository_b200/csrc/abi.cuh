@@ -63,8 +63,8 @@ int msp_destroy(msp_engine *e) { return engine_free(e); }
 int msp_rows(const msp_engine *e) { return e ? e->nb : -1; }
 int msp_spmv_format(const msp_engine *e, int *width) {
   if (!e) return -1;
-  if (width) *width = e->dval ? e->dia.nd : e->W;
-  return e->dval ? 1 : 0;
+  if (width) *width = (e->dval || e->dmask) ? e->dia.nd : e->W;
+  return e->dmask ? 2 : e->dval ? 1 : 0;
 }
 int msp_halo_size(const msp_engine *e) { return e ? e->H : -1; }
 

@@ -84,6 +84,7 @@ struct msp_engine {
   int *rp = nullptr, *ci = nullptr; double *va = nullptr; // strip CSR
   int *ecol = nullptr; double *eval = nullptr;            // ELL
   double *dval = nullptr; DiaOffsets dia{};               // DIA view (hot SpMV) when the strip has <= 8 diagonals
+  unsigned char *dmask = nullptr; double dconst[8] = {};  // coded DIA view (replaces dval) when every diagonal is constant
   int *brow = nullptr; int nbrow = 0;
   double *b = nullptr, *rhs = nullptr, *x = nullptr;
   double *halo[2] = {nullptr, nullptr}; // private copies of the neighbours' boundary layers
@@ -231,7 +232,19 @@ template <int MODE, bool RESID, bool SCALE, bool NORM>
 static void launch_spmv_w(msp_engine *e, const SpmvArgs &a, int ws_slot, GmresCtl *ctl_rw) {
   const long long items = ((long long)a.nb + 1) / 2;
   e->prof_begin(0, 12.0 * (double)e->nnz + 4.0 * (e->nb + 1) + 16.0 * e->nb + (RESID ? 8.0 * e->nb : 0.0));
-  if (a.dval) {
+  if (a.dmask) {
+    const long long quads = ((long long)a.nb + 3) / 4;
+    if (a.dia.nd == 5) {
+      auto k = k_spmv_cdia<5, MODE, RESID, SCALE, NORM>;
+      k<<<grid_for(quads, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
+    } else if (a.dia.nd == 7) {
+      auto k = k_spmv_cdia<7, MODE, RESID, SCALE, NORM>;
+      k<<<grid_for(quads, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
+    } else {
+      auto k = k_spmv_cdia<0, MODE, RESID, SCALE, NORM>;
+      k<<<grid_for(quads, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
+    }
+  } else if (a.dval) {
     if (a.dia.nd == 5) {
       auto k = k_spmv_dia<5, MODE, RESID, SCALE, NORM>;
       k<<<grid_for(items, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
@@ -259,7 +272,8 @@ static void launch_spmv_w(msp_engine *e, const SpmvArgs &a, int ws_slot, GmresCt
 static SpmvArgs spmv_args(msp_engine *e, const double *x, double *y) {
   SpmvArgs a{};
   a.nb = e->nb; a.W = e->W; a.H = e->H; a.ld = e->ld; a.ecol = e->ecol; a.eval = e->eval;
-  a.dval = e->dval; a.dia = e->dia;
+  a.dval = e->dval; a.dia = e->dia; a.dmask = e->dmask;
+  for (int k = 0; k < 8; k++) a.dconst[k] = e->dconst[k];
   a.x = x; a.y = y; a.lo = nullptr; a.hi = nullptr; a.b = nullptr; a.ctl = e->ctl; a.guard_it = -1;
   return a;
 }
@@ -310,7 +324,7 @@ static int engine_free(msp_engine *e) {
   for (auto &kv : e->cycle_graphs) cudaGraphExecDestroy(kv.second.exec);
   for (int J = 0; J < MSP_MAX_BLOCKS; J++)
     if (e->peer_any[J].base && e->peer_any_ipc[J]) cudaIpcCloseMemHandle(e->peer_any[J].base);
-  void *ptrs[] = {e->rp, e->ci, e->va, e->ecol, e->eval, e->dval, e->brow, e->b, e->rhs, e->x, e->halo[0], e->halo[1], e->V, e->Wb[0],
+  void *ptrs[] = {e->rp, e->ci, e->va, e->ecol, e->eval, e->dval, e->dmask, e->brow, e->b, e->rhs, e->x, e->halo[0], e->halo[1], e->V, e->Wb[0],
                   e->Wb[1], e->S, e->Slo, e->Shi, e->R, e->ctl, e->ws.partial, e->ws.counter, e->dsc, e->dfac, e->gram_partial, e->win.base, e->cd, e->aint, e->dec};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (e->hsc) cudaFreeHost(e->hsc);
@@ -403,6 +417,31 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
       cudaMemsetAsync(e->dval, 0, bytes, e->st);
       k_csr_to_dia<<<grid_for(e->nb, 16), MSPK_THREADS, 0, e->st>>>(e->nb, e->ld, e->off, e->rp, e->ci, e->va, e->dia, e->dval);
       cudaStreamSynchronize(e->st);
+      // ---- coded DIA: is every diagonal one constant wherever it is present?  Then one presence byte per row replaces
+      // the 8 ND bytes of values (same doubles enter the same fma chain: bit-identical products)
+      if (getenv("MSPLIT_NO_CDIA") == nullptr) {
+        unsigned long long *slot = nullptr; int *nonconst = nullptr;
+        unsigned long long hslot[8]; int hnon = 0;
+        for (int k = 0; k < 8; k++) hslot[k] = MSPK_DIA_UNSET;
+        if (cudaMalloc(&slot, sizeof(hslot)) != cudaSuccess || cudaMalloc(&nonconst, sizeof(int)) != cudaSuccess) { g_err = "oom"; return fail(1); }
+        cudaMemcpyAsync(slot, hslot, sizeof(hslot), cudaMemcpyHostToDevice, e->st);
+        cudaMemsetAsync(nonconst, 0, sizeof(int), e->st);
+        k_dia_probe_const<<<grid_for(e->nb, 16), MSPK_THREADS, 0, e->st>>>(e->nb, e->ld, e->dia.nd, e->dval, slot, nonconst);
+        cudaMemcpyAsync(&hnon, nonconst, sizeof(int), cudaMemcpyDeviceToHost, e->st);
+        cudaMemcpyAsync(hslot, slot, sizeof(hslot), cudaMemcpyDeviceToHost, e->st);
+        cudaStreamSynchronize(e->st);
+        if (!hnon) {
+          for (int k = 0; k < 8; k++) if (hslot[k] == MSPK_DIA_UNSET) hslot[k] = 0ULL; // diagonal of explicit zeros only
+          cudaMemcpyAsync(slot, hslot, sizeof(hslot), cudaMemcpyHostToDevice, e->st);
+          if (cudaMalloc(&e->dmask, (size_t)e->ld) != cudaSuccess) { g_err = "out of device memory (coded DIA)"; return fail(1); }
+          cudaMemsetAsync(e->dmask, 0, (size_t)e->ld, e->st);
+          k_dia_to_mask<<<grid_for(e->nb, 16), MSPK_THREADS, 0, e->st>>>(e->nb, e->ld, e->dia.nd, e->dval, slot, e->dmask);
+          cudaStreamSynchronize(e->st);
+          for (int k = 0; k < 8; k++) memcpy(&e->dconst[k], &hslot[k], sizeof(double));
+          cudaFree(e->dval); e->dval = nullptr;
+        }
+        cudaFree(slot); cudaFree(nonconst);
+      }
     }
   }
   if (!p->keep_csr) {

@@ -87,10 +87,15 @@ class Engine:
         self.H = _lib.lib().msp_halo_size(self.h)
 
     def spmv_format(self):
-        """("dia" | "ell", width) of the storage the hot SpMV reads."""
+        """("cdia" | "dia" | "ell", width) of the storage the hot SpMV reads."""
         w = C.c_int()
         kind = _lib.lib().msp_spmv_format(self.h, C.byref(w))
-        return ("dia" if kind == 1 else "ell"), w.value
+        return {2: "cdia", 1: "dia"}.get(kind, "ell"), w.value
+
+    @staticmethod
+    def spmv_bytes_per_row(fmt, width):
+        """Bytes per row the SpMV of that storage streams (matrix + x once + y once)."""
+        return {"cdia": 1.0, "dia": 8.0 * width, "ell": 12.0 * width}[fmt] + 16.0
 
     def close(self):
         if self._owner is None and getattr(self, "h", None):

@@ -1,5 +1,5 @@
 """Micro-benchmark of the hot kernels on resident data: algorithmic GB/s per SURVEY.md §8(d).
-usage: python tools/kbench.py [N] [restart]   (2-D N x N, one block on cuda:0)"""
+usage: python tools/kbench.py [N | MxN] [restart] [3d]   (2-D N x N or M x N, or 3-D N^3; one block on cuda:0)"""
 import json
 import os
 import sys
@@ -7,7 +7,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from medane_tchakorom_ufc_thesis_repository_b200 import solver as S  # noqa: E402
 
-N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+shape = sys.argv[1] if len(sys.argv) > 1 else "4096"
+M, N = (int(t) for t in shape.split("x")) if "x" in shape else (int(shape), int(shape))
 restart = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 dim3 = len(sys.argv) > 3 and sys.argv[3] == "3d"
 peak = 6453.1
@@ -19,10 +20,10 @@ if dim3:
     e = S.Engine(N, N, N, s=5, max_restart=restart)
     W = 7
 else:
-    e = S.Engine(N, N, s=5, max_restart=restart)
+    e = S.Engine(M, N, s=5, max_restart=restart)
     W = 5
 n = e.nb
-nnz = (5 * N * N - 4 * N) if not dim3 else (7 * N ** 3 - 6 * N * N)
+nnz = (5 * M * N - 2 * M - 2 * N) if not dim3 else (7 * N ** 3 - 6 * N * N)
 rows = []
 
 
@@ -36,7 +37,7 @@ rec("copy (STREAM)", e.bench_kernel(4, iters=20), 16 * n)
 fmt, width = e.spmv_format()
 ms = e.bench_kernel(0, iters=20)
 rec(f"spmv {fmt.upper()} [CSR bytes]", ms, 12 * nnz + 4 * (n + 1) + 16 * n)
-rec(f"spmv {fmt.upper()} [own {width}-wide bytes]", ms, ((8 if fmt == "dia" else 12) * width + 16) * n)
+rec(f"spmv {fmt.upper()} [own {width}-wide bytes]", ms, S.Engine.spmv_bytes_per_row(fmt, width) * n)
 ms = e.bench_kernel(5, iters=20)
 rec("spmv, input scaled on the fly", ms, 12 * nnz + 4 * (n + 1) + 16 * n)
 for nv in (1, 2, 4, 8, 9, 16, 24, 30):
@@ -50,4 +51,5 @@ for nv in (1, 4, 8, 16, 30):
 rec("gram [R|b]^T[R|b] 6 columns", e.bench_kernel(6, 6, iters=10), 8 * n * 6)
 rec("spmm s=5", e.bench_kernel(3, 5, iters=10), 12 * nnz + 4 * n + 8 * n * 5 + 8 * n * 5)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump({"N": N, "dim": 3 if dim3 else 2, "rows": rows}, open(f"gpurun_out/kbench_{N}{'_3d' if dim3 else ''}.json", "w"), indent=1)
+json.dump({"shape": shape, "dim": 3 if dim3 else 2, "spmv_format": fmt, "rows": rows},
+          open(f"gpurun_out/kbench_{shape}{'_3d' if dim3 else ''}.json", "w"), indent=1)
