@@ -85,6 +85,7 @@ struct msp_engine {
   int *ecol = nullptr; double *eval = nullptr;            // ELL
   double *dval = nullptr; DiaOffsets dia{};               // DIA view (hot SpMV) when the strip has <= 8 diagonals
   unsigned char *dmask = nullptr; double dconst[8] = {};  // coded DIA view (replaces dval) when every diagonal is constant
+  bool dia_stencil = false;                               // coded DIA with offsets (.., -D, -1, 0, +1, +D, ..), D % 4 == 0
   int *brow = nullptr; int nbrow = 0;
   double *b = nullptr, *rhs = nullptr, *x = nullptr;
   double *halo[2] = {nullptr, nullptr}; // private copies of the neighbours' boundary layers
@@ -232,7 +233,17 @@ template <int MODE, bool RESID, bool SCALE, bool NORM>
 static void launch_spmv_w(msp_engine *e, const SpmvArgs &a, int ws_slot, GmresCtl *ctl_rw) {
   const long long items = ((long long)a.nb + 1) / 2;
   e->prof_begin(0, 12.0 * (double)e->nnz + 4.0 * (e->nb + 1) + 16.0 * e->nb + (RESID ? 8.0 * e->nb : 0.0));
-  if (a.dmask) {
+  const bool al32 = (((uintptr_t)a.x | (uintptr_t)a.y | (uintptr_t)(RESID ? a.b : nullptr)) & 31) == 0;
+  if (a.dmask && a.stencil && al32) {
+    const long long quads = ((long long)a.nb + 3) / 4;
+    if (a.dia.nd == 5) {
+      auto k = k_spmv_cdia_stencil<5, MODE, RESID, SCALE, NORM>;
+      k<<<grid_for(quads, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
+    } else {
+      auto k = k_spmv_cdia_stencil<7, MODE, RESID, SCALE, NORM>;
+      k<<<grid_for(quads, resident_blocks_per_sm(k)), MSPK_THREADS, 0, e->st>>>(a, e->ws, ws_slot, ctl_rw);
+    }
+  } else if (a.dmask) {
     const long long quads = ((long long)a.nb + 3) / 4;
     if (a.dia.nd == 5) {
       auto k = k_spmv_cdia<5, MODE, RESID, SCALE, NORM>;
@@ -272,7 +283,7 @@ static void launch_spmv_w(msp_engine *e, const SpmvArgs &a, int ws_slot, GmresCt
 static SpmvArgs spmv_args(msp_engine *e, const double *x, double *y) {
   SpmvArgs a{};
   a.nb = e->nb; a.W = e->W; a.H = e->H; a.ld = e->ld; a.ecol = e->ecol; a.eval = e->eval;
-  a.dval = e->dval; a.dia = e->dia; a.dmask = e->dmask;
+  a.dval = e->dval; a.dia = e->dia; a.dmask = e->dmask; a.stencil = e->dia_stencil ? 1 : 0;
   for (int k = 0; k < 8; k++) a.dconst[k] = e->dconst[k];
   a.x = x; a.y = y; a.lo = nullptr; a.hi = nullptr; a.b = nullptr; a.ctl = e->ctl; a.guard_it = -1;
   return a;
@@ -439,6 +450,11 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
           cudaStreamSynchronize(e->st);
           for (int k = 0; k < 8; k++) memcpy(&e->dconst[k], &hslot[k], sizeof(double));
           cudaFree(e->dval); e->dval = nullptr;
+          // stencil shape: (.., -D, -1, 0, +1, +D, ..), far offsets multiples of 4 => k_spmv_cdia_stencil
+          const int nd = e->dia.nd, c = nd / 2;
+          bool st = (nd == 5 || nd == 7) && e->nb >= 4 && e->dia.off[c] == 0 && e->dia.off[c - 1] == -1 && e->dia.off[c + 1] == 1;
+          for (int k = 0; st && k < nd; k++) if ((k < c - 1 || k > c + 1) && (e->dia.off[k] & 3) != 0) st = false;
+          e->dia_stencil = st && getenv("MSPLIT_NO_STENCIL") == nullptr;
         }
         cudaFree(slot); cudaFree(nonconst);
       }

@@ -355,6 +355,7 @@ struct SpmvArgs {
   const double *dval;   // DIA values (slot-major), or null
   DiaOffsets dia;
   const unsigned char *dmask; // coded DIA: one presence byte per row (bit k = diagonal k holds its constant), or null
+  int stencil;          // coded DIA: offsets are (.., -D, -1, 0, +1, +D, ..) with every far offset a multiple of 4
   double dconst[8];     // coded DIA: the constant of every diagonal
   const double *x;      // input (own rows)
   const double *lo, *hi; // neighbour boundaries (MODE 1), may be null
@@ -475,19 +476,21 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_spmv_dia(SpmvArgs a, ReduceWs 
   if (NORM) spmv_norm_epilogue(nrm, ws, ws_slot, ctl_rw);
 }
 
-// Coded-DIA SpMV: same contract, template flags and epilogue as k_spmv_ell / k_spmv_dia.  Four rows per thread:
-// one 32-bit load brings their presence bytes, x is read with the widest aligned load the diagonal's offset allows
-// (256-bit when off % 4 == 0, 2 x 128-bit when even, 64/128/64 when odd; all L1-cached — neighbouring threads and
-// diagonals share lines), y leaves with one 256-bit store.  Algorithmic traffic 17 bytes per row.
+// Coded-DIA SpMV, general form: same contract, template flags and epilogue as k_spmv_ell / k_spmv_dia.  Four rows per
+// thread: one 32-bit load brings their presence bytes, x is read with the widest aligned load the diagonal's offset
+// allows (256-bit when off % 4 == 0, 2 x 128-bit when even, 64/128/64 when odd; all L1-cached), y leaves with one
+// 256-bit store.  Algorithmic traffic 17 bytes per row.  L1-wavefront-bound (ncu: 88 %, 0.214 ms at 67 M rows) because
+// of the odd offsets and of its per-diagonal branches; stencil-shaped strips take k_spmv_cdia_stencil below.
 __device__ __forceinline__ void ld4_cached(const double *p, double (&v)[4]) {
-  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+  asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
 __device__ __forceinline__ void st4(double *p, const double (&v)[4]) {
   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
+// x[c .. c+3] for the rows r .. r+3 of one thread (nvalid of them exist); entries of missing rows are 0
 template <int MODE>
-__device__ __forceinline__ void gather_x4(const SpmvArgs &a, int c, bool x_al32, double inv, bool scale, double (&xv)[4]) {
-  if (c >= 0 && c + 3 < a.nb) {           // all four columns are own rows
+__device__ __forceinline__ void gather_x4(const SpmvArgs &a, int c, int nvalid, bool x_al32, double inv, bool scale, double (&xv)[4]) {
+  if (nvalid == 4 && c >= 0 && c + 3 < a.nb) { // all four columns are own rows
     if ((c & 3) == 0 && x_al32) {
       ld4_cached(a.x + c, xv);
     } else if ((c & 1) == 0 && x_al32) {
@@ -509,7 +512,7 @@ __device__ __forceinline__ void gather_x4(const SpmvArgs &a, int c, bool x_al32,
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; i++) xv[i] = gather_x<MODE>(a, c + i, inv, scale);
+    for (int i = 0; i < 4; i++) xv[i] = (i < nvalid) ? gather_x<MODE>(a, c + i, inv, scale) : 0.0;
   }
 }
 template <int ND_T, int MODE, bool RESID, bool SCALE, bool NORM>
@@ -526,17 +529,18 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_spmv_cdia(SpmvArgs a, ReduceWs
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nquads; q += (long long)gridDim.x * blockDim.x) {
     const long long r = q * 4;
     const unsigned m = __ldg(reinterpret_cast<const unsigned *>(a.dmask) + q); // rows >= nb: byte 0
+    const int nvalid = (a.nb - r < 4) ? (int)(a.nb - r) : 4;
     double s[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int k = 0; k < ((ND_T > 0) ? ND_T : 8); k++) {
       if (ND_T == 0 && k >= ND) break;
       const double ck = a.dconst[k];
       double xv[4];
-      gather_x4<MODE>(a, (int)r + a.dia.off[k], x_al32, inv, SCALE, xv);
+      gather_x4<MODE>(a, (int)r + a.dia.off[k], nvalid, x_al32, inv, SCALE, xv);
 #pragma unroll
       for (int i = 0; i < 4; i++) s[i] = fma(((m >> (8 * i + k)) & 1u) ? ck : 0.0, xv[i], s[i]);
     }
-    if (r + 3 < a.nb) {
+    if (nvalid == 4) {
       if (RESID) {
         double bv[4];
         if ((reinterpret_cast<uintptr_t>(a.b) & 31) == 0) ld4_cached(a.b + r, bv);
@@ -557,7 +561,107 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_spmv_cdia(SpmvArgs a, ReduceWs
     } else {
 #pragma unroll
       for (int i = 0; i < 4; i++)
-        if (r + i < a.nb) {
+        if (i < nvalid) {
+          if (RESID) s[i] = a.b[r + i] - s[i];
+          a.y[r + i] = s[i];
+          if (NORM) nrm = fma(s[i], s[i], nrm);
+        }
+    }
+  }
+  if (NORM) spmv_norm_epilogue(nrm, ws, ws_slot, ctl_rw);
+}
+
+// Coded-DIA SpMV for stencil-shaped strips: ND = 5 / 7 diagonals at offsets (.., -D, -1, 0, +1, +D, ..) with every far
+// offset a multiple of 4 (checked on the host: e->dia_stencil).  Knowing the shape at compile time makes the body
+// branch-free until all loads are in flight: the thread's own x quad and one aligned quad per far diagonal leave as
+// 256-bit loads back to back (addresses clamped into the block; the few quads whose far columns fall outside it, or
+// into a neighbour's boundary layer, are patched afterwards through gather_x), the +-1 diagonals take x[r-1] / x[r+4]
+// from the neighbouring lanes by shuffle (edge lanes fetch them), then the fma chains run in diagonal order — the same
+// doubles in the same order as the CSR chain.  Per 128 rows: (ND - 2) x 8 L1 wavefronts of loads + 8 of stores.
+template <int ND, int MODE, bool RESID, bool SCALE, bool NORM>
+__global__ void __launch_bounds__(MSPK_THREADS, (RESID || MODE != 0) ? 1 : (ND == 5 ? 5 : 4)) k_spmv_cdia_stencil(SpmvArgs a, ReduceWs ws, int ws_slot, GmresCtl *ctl_rw) {
+  if (a.guard_it >= 0) {
+    if (!a.ctl->active || a.ctl->it != a.guard_it) return;
+  }
+  constexpr int C = ND / 2;   // main diagonal; C - 1 / C + 1 are the -1 / +1 neighbours
+  constexpr int NF = ND - 3;  // far diagonals
+  const double inv = SCALE ? a.ctl->inv_arr[a.guard_it > 0 ? a.guard_it : 0] : 1.0;
+  const int lane = threadIdx.x & 31;
+  const int last4 = (a.nb - 4) & ~3; // last aligned quad that lies inside the block (nb >= 4)
+  double nrm = 0.0;
+  const long long nquads = ((long long)a.nb + 3) >> 2;
+  // the trip count is uniform over a warp (the lanes exchange x entries by shuffle); lanes past the end idle.
+  // (Tried and dropped: one contiguous row range per block instead of the grid stride, hoping for L1 hits on the +-nx
+  // diagonals — 0.33 ms instead of 0.19 ms at 67 M rows: the +-D quads then miss L2 as well.)
+  for (long long q0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x - lane); q0 < nquads; q0 += (long long)gridDim.x * blockDim.x) {
+    const long long q = q0 + lane;
+    const long long r = q * 4;
+    const int nvalid = (q < nquads) ? (int)((a.nb - r < 4) ? (a.nb - r) : 4) : 0;
+    // ---- all loads first
+    double own[4], far[NF][4], bv[4];
+    int cf[NF];
+    ld4_cached(a.x + ((r < last4) ? (int)r : last4), own);
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      cf[f] = (int)r + a.dia.off[(f < C - 1) ? f : f + 3];
+      ld4_cached(a.x + min(max(cf[f], 0), last4), far[f]);
+    }
+    if (RESID) ld4_cached(a.b + ((r < last4) ? (int)r : last4), bv);
+    const unsigned m = nvalid ? __ldg(reinterpret_cast<const unsigned *>(a.dmask) + q) : 0u;
+    // ---- own quad, its two outer neighbours
+    if (SCALE) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) own[i] = own[i] * inv;
+    }
+    if (nvalid != 4) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) own[i] = (i < nvalid) ? gather_x<MODE>(a, (int)r + i, inv, SCALE) : 0.0;
+    }
+    double xm1 = __shfl_up_sync(0xffffffffu, own[3], 1);
+    double xp4 = __shfl_down_sync(0xffffffffu, own[0], 1);
+    if (nvalid && lane == 0) xm1 = gather_x<MODE>(a, (int)r - 1, inv, SCALE);
+    if (nvalid == 4) {
+      if (lane == 31 || r + 4 >= a.nb) xp4 = gather_x<MODE>(a, (int)r + 4, inv, SCALE); // the next lane holds no row
+    } else xp4 = 0.0; // only row r + 3 would use it
+    // ---- far diagonals: patch the quads that are not four own rows
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+      if (SCALE) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) far[f][i] = far[f][i] * inv;
+      }
+      if (nvalid != 4 || cf[f] < 0 || cf[f] + 3 >= a.nb) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) far[f][i] = (i < nvalid) ? gather_x<MODE>(a, cf[f] + i, inv, SCALE) : 0.0;
+      }
+    }
+    // ---- fma chains in diagonal (= sorted column) order
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < ND; k++) {
+      const double ck = a.dconst[k];
+      double xv[4];
+      if (k == C) { xv[0] = own[0]; xv[1] = own[1]; xv[2] = own[2]; xv[3] = own[3]; }
+      else if (k == C - 1) { xv[0] = xm1; xv[1] = own[0]; xv[2] = own[1]; xv[3] = own[2]; }
+      else if (k == C + 1) { xv[0] = own[1]; xv[1] = own[2]; xv[2] = own[3]; xv[3] = xp4; }
+      else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) xv[i] = far[(k < C) ? k : k - 3][i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) s[i] = fma(((m >> (8 * i + k)) & 1u) ? ck : 0.0, xv[i], s[i]);
+    }
+    if (nvalid == 4) {
+      if (RESID) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) s[i] = bv[i] - s[i];
+      }
+      st4(a.y + r, s);
+      if (NORM) { nrm = fma(s[0], s[0], fma(s[1], s[1], nrm)); nrm = fma(s[2], s[2], fma(s[3], s[3], nrm)); }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (i < nvalid) {
           if (RESID) s[i] = a.b[r + i] - s[i];
           a.y[r + i] = s[i];
           if (NORM) nrm = fma(s[i], s[i], nrm);
