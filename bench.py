@@ -8,8 +8,8 @@ inner GMRES(30) capped at max_it 20 (rtol 1e-10, initial-residual norm), exact l
 A "step" is ONE OUTER ITERATION of the reference's do { } while loop (…-minimization-global.c:288-363):
 s x (updateLocalRHS, inner GMRES solve of <= 20 Arnoldi steps, boundary exchange, S[:,t] = x), then
 R = A S, the least-squares solve and x = S alpha.  The time-to-rtol-1e-6 the metric names is
-outer_iterations x (seconds per outer iteration); the oracle shows this configuration needs ~2.6e3 outer
-iterations at one block (N^1.55 growth), i.e. far longer than a benchmark run, so the
+outer_iterations x (seconds per outer iteration); the oracle shows this configuration needs ~3e3 outer
+iterations at one block (x3.2 per doubling of the edge: 939 measured at 4096^2), i.e. far longer than a benchmark run, so the
 bench times K outer iterations and reports seconds per outer iteration (strong scaling: the problem is
 fixed, blocks = GPUs).  `--to-rtol` runs the real thing to convergence on a smaller grid.
 
@@ -266,7 +266,7 @@ def run_gpu(args):
         "config": workload_config(args, world),
         "time_to_rtol": {"reached": bool(rel <= RTOL), "rel_residual_after_timed_steps": rel,
                          "outer_iterations_so_far": args.warmup + k_done,
-                         "note": "time-to-rtol 1e-6 = outer iterations x value; ~2.6e3 outer iterations extrapolated at 1 block (DESIGN.md §6)"},
+                         "note": "time-to-rtol 1e-6 = outer iterations x value; ~3e3 outer iterations extrapolated at 1 block from 939 measured at 4096^2 (DESIGN.md §6)"},
         "wall_s_timed_region": wall,
         "clocks": clocks,
         "roofline": roofline,
