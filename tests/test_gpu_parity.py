@@ -242,6 +242,37 @@ def test_inner_solver_semantics(S, oracle):
 
 
 # ------------------------------------------------------------------ minimisation pieces
+@pytest.mark.parametrize("dims,G,K,kind", [((24, 16, 1), 3, 1, "SMSM_GLOBAL"), ((24, 16, 1), 3, 1, "SMSM_LOCAL"), ((8, 8, 6), 2, 0, "SMSM_GLOBAL"),
+                                           ((37, 21, 1), 1, 0, "SMSM_GLOBAL")])
+def test_spmm_coded_dia_sweeps_identical_to_ell_spmm(S, monkeypatch, dims, G, K, kind):
+    """R = A S: with the coded DIA view the engine sweeps the SpMV over the s columns; with MSPLIT_NO_DIA it runs the one-pass
+    ELL SpMM kernel.  Same fma chain per row => the local QR factor of [R | b] is bit-identical."""
+    rng = np.random.default_rng(21)
+    m, n, p = dims
+    s = 5
+    got = {}
+    Sg = None
+    for env in (None, "MSPLIT_NO_DIA"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        e = S.Engine(m, n, p, block=K, nblocks=G, s=s)
+        if env:
+            monkeypatch.delenv(env)
+        nb, H = e.nb, e.H
+        if Sg is None:
+            Sg = rng.standard_normal((s, nb + 2 * H))
+        for t in range(s):
+            e.x = Sg[t, H:H + nb]
+            if K > 0: e.set_halo(0, Sg[t, :H])
+            if K < G - 1: e.set_halo(1, Sg[t, H + nb:])
+            e.push_iterate(t)
+        e.spmm_AS(kind)
+        got[e.spmv_format()[0]] = np.array(e.minimize_local_qr(kind))
+        e.close()
+    assert set(got) == {"cdia", "ell"}
+    assert np.array_equal(got["cdia"], got["ell"])
+
+
 def test_tsqr_minimisation_matches_lstsq(S, oracle):
     rng = np.random.default_rng(11)
     m, n, G, s = 24, 16, 2, 5
