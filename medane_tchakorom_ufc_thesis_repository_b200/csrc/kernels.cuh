@@ -15,6 +15,10 @@
 #define MSPK_MAXK 64     // max restart
 #define MSPK_THREADS 256
 #define MSPK_MAX_PART 2048
+#ifndef MSPK_CDIA_MINB5
+#define MSPK_CDIA_MINB5 4   // resident blocks per SM the hot coded-DIA SpMV is compiled for (64 registers; measured: 5 blocks = 48 registers spills and loses 20 %, uncapped 98+ registers loses 25 %)
+#define MSPK_CDIA_MINB7 4
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // device-resident GMRES control block (KSP_GMRES of PETSc: HH, cc/ss rotations, GRS, convergence
@@ -572,22 +576,122 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_spmv_cdia(SpmvArgs a, ReduceWs
 }
 
 // Coded-DIA SpMV for stencil-shaped strips: ND = 5 / 7 diagonals at offsets (.., -D, -1, 0, +1, +D, ..) with every far
-// offset a multiple of 4 (checked on the host: e->dia_stencil).  Knowing the shape at compile time makes the body
-// branch-free until all loads are in flight: the thread's own x quad and one aligned quad per far diagonal leave as
-// 256-bit loads back to back (addresses clamped into the block; the few quads whose far columns fall outside it, or
-// into a neighbour's boundary layer, are patched afterwards through gather_x), the +-1 diagonals take x[r-1] / x[r+4]
-// from the neighbouring lanes by shuffle (edge lanes fetch them), then the fma chains run in diagonal order — the same
-// doubles in the same order as the CSR chain.  Per 128 rows: (ND - 2) x 8 L1 wavefronts of loads + 8 of stores.
+// offset a multiple of 4 (checked on the host: e->dia_stencil).  Four rows per thread.  All loads of a trip leave back
+// to back before anything depends on them: the thread's own x quad and one aligned quad per far diagonal as 256-bit
+// loads, the presence bytes, and on the warp's edge lanes x[r-1] / x[r+4]; the other lanes take those two from their
+// neighbours by shuffle.  Then the fma chains run in diagonal order — the same doubles in the same order as the CSR
+// chain.  Per 128 rows: (ND - 2) x 8 L1 wavefronts of loads + 8 of stores.
+//   Two warp-uniform specialisations keep the instruction count down (the first version issued ~280 instructions per
+//   trip for 7 diagonals and ncu showed 61 % issue utilisation next to 50 % DRAM):
+//   * INTERIOR — every column any lane touches is an own row of a complete quad: no clamping, no patching;
+//     otherwise addresses are clamped into the block and the quads whose columns fall outside it (or into a
+//     neighbour's boundary layer) are patched through gather_x;
+//   * all presence bytes of the warp full (no domain face among its 128 rows): plain fma chain, no selects.
+template <int ND, int MODE, bool RESID, bool SCALE, bool NORM, bool INTERIOR>
+__device__ __forceinline__ void cdia_stencil_trip(const SpmvArgs &a, long long q, int nvalid, int lane, double inv, int last4, double &nrm) {
+  constexpr int C = ND / 2;   // main diagonal; C - 1 / C + 1 are the -1 / +1 neighbours
+  constexpr int NF = ND - 3;  // far diagonals
+  constexpr unsigned FULL = (ND == 5) ? 0x1f1f1f1fu : 0x7f7f7f7fu;
+  const long long r = q * 4;
+  // ---- all loads first
+  double own[4], far[NF][4], bv[4], xm1, xp4;
+  int cf[NF];
+  const int rc = INTERIOR ? (int)r : ((r < last4) ? (int)r : last4);
+  ld4_cached(a.x + rc, own);
+#pragma unroll
+  for (int f = 0; f < NF; f++) {
+    cf[f] = (int)r + a.dia.off[(f < C - 1) ? f : f + 3];
+    ld4_cached(a.x + (INTERIOR ? cf[f] : min(max(cf[f], 0), last4)), far[f]);
+  }
+  if (RESID) ld4_cached(a.b + rc, bv);
+  const unsigned m = (INTERIOR || nvalid) ? __ldg(reinterpret_cast<const unsigned *>(a.dmask) + q) : 0u;
+  double edge = 0.0;
+  if (INTERIOR) { // one predicated load (never a branch: it must leave with the others, not after the first use of `own`)
+    const double *pe = a.x + r + ((lane == 0) ? -1 : 4);
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.f64 %0, [%1];\n\t}" : "+d"(edge) : "l"(pe), "r"((int)(lane == 0 || lane == 31)));
+  }
+  // ---- own quad and its two outer neighbours
+  if (SCALE) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) own[i] = own[i] * inv;
+    if (INTERIOR) edge = edge * inv;
+  }
+  if (!INTERIOR && nvalid != 4) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) own[i] = (i < nvalid) ? gather_x<MODE>(a, (int)r + i, inv, SCALE) : 0.0;
+  }
+  {
+    const double up = __shfl_up_sync(0xffffffffu, own[3], 1), dn = __shfl_down_sync(0xffffffffu, own[0], 1);
+    xm1 = (INTERIOR && lane == 0) ? edge : up;
+    xp4 = (INTERIOR && lane == 31) ? edge : dn;
+  }
+  if (!INTERIOR) {
+    if (nvalid && lane == 0) xm1 = gather_x<MODE>(a, (int)r - 1, inv, SCALE);
+    if (nvalid == 4) {
+      if (lane == 31 || r + 4 >= a.nb) xp4 = gather_x<MODE>(a, (int)r + 4, inv, SCALE); // the next lane holds no row
+    } else xp4 = 0.0; // only row r + 3 would use it
+  }
+  // ---- far diagonals
+#pragma unroll
+  for (int f = 0; f < NF; f++) {
+    if (SCALE) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) far[f][i] = far[f][i] * inv;
+    }
+    if (!INTERIOR && (nvalid != 4 || cf[f] < 0 || cf[f] + 3 >= a.nb)) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) far[f][i] = (i < nvalid) ? gather_x<MODE>(a, cf[f] + i, inv, SCALE) : 0.0;
+    }
+  }
+  // ---- fma chains in diagonal (= sorted column) order
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  const bool full = INTERIOR && __all_sync(0xffffffffu, m == FULL);
+#pragma unroll
+  for (int k = 0; k < ND; k++) {
+    const double ck = a.dconst[k];
+    double xv[4];
+    if (k == C) { xv[0] = own[0]; xv[1] = own[1]; xv[2] = own[2]; xv[3] = own[3]; }
+    else if (k == C - 1) { xv[0] = xm1; xv[1] = own[0]; xv[2] = own[1]; xv[3] = own[2]; }
+    else if (k == C + 1) { xv[0] = own[1]; xv[1] = own[2]; xv[2] = own[3]; xv[3] = xp4; }
+    else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) xv[i] = far[(k < C) ? k : k - 3][i];
+    }
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) s[i] = fma(ck, xv[i], s[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) s[i] = fma(((m >> (8 * i + k)) & 1u) ? ck : 0.0, xv[i], s[i]);
+    }
+  }
+  if (INTERIOR || nvalid == 4) {
+    if (RESID) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) s[i] = bv[i] - s[i];
+    }
+    st4(a.y + r, s);
+    if (NORM) { nrm = fma(s[0], s[0], fma(s[1], s[1], nrm)); nrm = fma(s[2], s[2], fma(s[3], s[3], nrm)); }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (i < nvalid) {
+        if (RESID) s[i] = a.b[r + i] - s[i];
+        a.y[r + i] = s[i];
+        if (NORM) nrm = fma(s[i], s[i], nrm);
+      }
+  }
+}
 template <int ND, int MODE, bool RESID, bool SCALE, bool NORM>
-__global__ void __launch_bounds__(MSPK_THREADS, (RESID || MODE != 0) ? 1 : (ND == 5 ? 5 : 4)) k_spmv_cdia_stencil(SpmvArgs a, ReduceWs ws, int ws_slot, GmresCtl *ctl_rw) {
+__global__ void __launch_bounds__(MSPK_THREADS, (RESID || MODE != 0) ? 1 : (ND == 5 ? MSPK_CDIA_MINB5 : MSPK_CDIA_MINB7)) k_spmv_cdia_stencil(SpmvArgs a, ReduceWs ws, int ws_slot, GmresCtl *ctl_rw) {
   if (a.guard_it >= 0) {
     if (!a.ctl->active || a.ctl->it != a.guard_it) return;
   }
-  constexpr int C = ND / 2;   // main diagonal; C - 1 / C + 1 are the -1 / +1 neighbours
-  constexpr int NF = ND - 3;  // far diagonals
   const double inv = SCALE ? a.ctl->inv_arr[a.guard_it > 0 ? a.guard_it : 0] : 1.0;
   const int lane = threadIdx.x & 31;
   const int last4 = (a.nb - 4) & ~3; // last aligned quad that lies inside the block (nb >= 4)
+  // rows whose every column (own quad +- 1, far quads) is an own row of the block
+  const long long r_lo = -(long long)a.dia.off[0], r_hi = (long long)a.nb - 4 - a.dia.off[ND - 1];
   double nrm = 0.0;
   const long long nquads = ((long long)a.nb + 3) >> 2;
   // the trip count is uniform over a warp (the lanes exchange x entries by shuffle); lanes past the end idle.
@@ -595,78 +699,11 @@ __global__ void __launch_bounds__(MSPK_THREADS, (RESID || MODE != 0) ? 1 : (ND =
   // diagonals — 0.33 ms instead of 0.19 ms at 67 M rows: the +-D quads then miss L2 as well.)
   for (long long q0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x - lane); q0 < nquads; q0 += (long long)gridDim.x * blockDim.x) {
     const long long q = q0 + lane;
-    const long long r = q * 4;
-    const int nvalid = (q < nquads) ? (int)((a.nb - r < 4) ? (a.nb - r) : 4) : 0;
-    // ---- all loads first
-    double own[4], far[NF][4], bv[4];
-    int cf[NF];
-    ld4_cached(a.x + ((r < last4) ? (int)r : last4), own);
-#pragma unroll
-    for (int f = 0; f < NF; f++) {
-      cf[f] = (int)r + a.dia.off[(f < C - 1) ? f : f + 3];
-      ld4_cached(a.x + min(max(cf[f], 0), last4), far[f]);
-    }
-    if (RESID) ld4_cached(a.b + ((r < last4) ? (int)r : last4), bv);
-    const unsigned m = nvalid ? __ldg(reinterpret_cast<const unsigned *>(a.dmask) + q) : 0u;
-    // ---- own quad, its two outer neighbours
-    if (SCALE) {
-#pragma unroll
-      for (int i = 0; i < 4; i++) own[i] = own[i] * inv;
-    }
-    if (nvalid != 4) {
-#pragma unroll
-      for (int i = 0; i < 4; i++) own[i] = (i < nvalid) ? gather_x<MODE>(a, (int)r + i, inv, SCALE) : 0.0;
-    }
-    double xm1 = __shfl_up_sync(0xffffffffu, own[3], 1);
-    double xp4 = __shfl_down_sync(0xffffffffu, own[0], 1);
-    if (nvalid && lane == 0) xm1 = gather_x<MODE>(a, (int)r - 1, inv, SCALE);
-    if (nvalid == 4) {
-      if (lane == 31 || r + 4 >= a.nb) xp4 = gather_x<MODE>(a, (int)r + 4, inv, SCALE); // the next lane holds no row
-    } else xp4 = 0.0; // only row r + 3 would use it
-    // ---- far diagonals: patch the quads that are not four own rows
-#pragma unroll
-    for (int f = 0; f < NF; f++) {
-      if (SCALE) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) far[f][i] = far[f][i] * inv;
-      }
-      if (nvalid != 4 || cf[f] < 0 || cf[f] + 3 >= a.nb) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) far[f][i] = (i < nvalid) ? gather_x<MODE>(a, cf[f] + i, inv, SCALE) : 0.0;
-      }
-    }
-    // ---- fma chains in diagonal (= sorted column) order
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int k = 0; k < ND; k++) {
-      const double ck = a.dconst[k];
-      double xv[4];
-      if (k == C) { xv[0] = own[0]; xv[1] = own[1]; xv[2] = own[2]; xv[3] = own[3]; }
-      else if (k == C - 1) { xv[0] = xm1; xv[1] = own[0]; xv[2] = own[1]; xv[3] = own[2]; }
-      else if (k == C + 1) { xv[0] = own[1]; xv[1] = own[2]; xv[2] = own[3]; xv[3] = xp4; }
-      else {
-#pragma unroll
-        for (int i = 0; i < 4; i++) xv[i] = far[(k < C) ? k : k - 3][i];
-      }
-#pragma unroll
-      for (int i = 0; i < 4; i++) s[i] = fma(((m >> (8 * i + k)) & 1u) ? ck : 0.0, xv[i], s[i]);
-    }
-    if (nvalid == 4) {
-      if (RESID) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) s[i] = bv[i] - s[i];
-      }
-      st4(a.y + r, s);
-      if (NORM) { nrm = fma(s[0], s[0], fma(s[1], s[1], nrm)); nrm = fma(s[2], s[2], fma(s[3], s[3], nrm)); }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (i < nvalid) {
-          if (RESID) s[i] = a.b[r + i] - s[i];
-          a.y[r + i] = s[i];
-          if (NORM) nrm = fma(s[i], s[i], nrm);
-        }
-    }
+    const int nvalid = (q < nquads) ? (int)((a.nb - q * 4 < 4) ? (a.nb - q * 4) : 4) : 0;
+    // warp-uniform without a vote: first and last lane of the warp decide (rows are consecutive across the lanes)
+    const bool interior = (q0 * 4 >= r_lo) && ((q0 + 31) * 4 <= r_hi);
+    if (interior) cdia_stencil_trip<ND, MODE, RESID, SCALE, NORM, true>(a, q, 4, lane, inv, last4, nrm);
+    else cdia_stencil_trip<ND, MODE, RESID, SCALE, NORM, false>(a, q, nvalid, lane, inv, last4, nrm);
   }
   if (NORM) spmv_norm_epilogue(nrm, ws, ws_slot, ctl_rw);
 }
