@@ -241,6 +241,53 @@ def test_inner_solver_semantics(S, oracle):
     e.close()
 
 
+# ------------------------------------------------------------------ BASELINE's full sizes: size-independent properties
+@pytest.mark.parametrize("dims,G,K", [((8192, 8192, 1), 1, 0),       # configs[2] on one GPU: 67 108 864 rows
+                                      ((512, 512, 512), 8, 3)],      # configs[3]/[4]: the per-GPU slab of 512^3 on 8 GPUs
+                         ids=["2d-8192x8192", "3d-512cube-slab-3-of-8"])
+def test_full_size_properties(S, dims, G, K):
+    """Nothing the oracle could finish in seconds at these sizes, so the checks are properties of the operator itself:
+    b = A 1 has the closed form of the stencil (0 in the interior, one unit per missing neighbour), A 1 recomputed equals
+    b bit for bit, A_KK is symmetric (<A x, y> = <x, A y>), linear, and the solver's stopping quantity after two outer
+    iterations equals an independently recomputed ||b - A x||."""
+    m, n, p = dims
+    e = S.Engine(m, n, p, block=K, nblocks=G, s=5, max_restart=30)
+    nb, H = e.nb, e.H
+    assert nb == m * n * p // G and e.spmv_format()[0] == "cdia"
+    b = e.b
+    # closed form: every row sums to (number of missing neighbours); the strip form also misses nothing across blocks
+    idx = np.arange(K * nb, (K + 1) * nb, dtype=np.int64)
+    if p == 1:
+        i, j = idx // n, idx % n
+        expect = (i == 0).astype(np.float64) + (i == m - 1) + (j == 0) + (j == n - 1)
+    else:
+        i, j, k = idx % m, (idx // m) % n, idx // (m * n)
+        expect = (i == 0).astype(np.float64) + (i == m - 1) + (j == 0) + (j == n - 1) + (k == 0) + (k == p - 1)
+    assert np.array_equal(b, expect)
+    del idx, expect
+    ones_lo = np.ones(H) if K > 0 else None
+    ones_hi = np.ones(H) if K < G - 1 else None
+    assert np.array_equal(e.spmv(S.MAT_STRIP, np.ones(nb), ones_lo, ones_hi), b)
+    rng = np.random.default_rng(2026)
+    x = rng.standard_normal(nb)
+    y = rng.standard_normal(nb)
+    Ax, Ay = e.spmv(S.MAT_DIAG, x), e.spmv(S.MAT_DIAG, y)
+    assert abs(np.dot(Ax, y) - np.dot(x, Ay)) <= 1e-11 * np.linalg.norm(Ax) * np.linalg.norm(y)
+    Az = e.spmv(S.MAT_DIAG, 2.0 * x - y)
+    assert np.linalg.norm(Az - (2.0 * Ax - Ay)) <= 1e-14 * np.linalg.norm(Az)
+    del Ax, Ay, Az, y
+    if G == 1:
+        res = e.solve("SMSM_GLOBAL", s=5, rtol=1e-6, inner=S.ksp_opts(restart=30, max_it=20, rtol=1e-10, abstol=1e-100), max_outer=2)
+        assert res["outer_its"] == 2 and res["hist"][1] < res["hist"][0] < res["norm0"]
+        xs = e.x
+        r = b - e.spmv(S.MAT_DIAG, xs)
+        true = np.linalg.norm(r)
+        assert abs(res["final_residual"] - true) <= 1e-10 * true
+        # the minimiser's residual estimate (last diagonal entry of the TSQR factor) IS the true residual
+        assert abs(res["hist"][1] - true) <= 1e-8 * true
+    e.close()
+
+
 # ------------------------------------------------------------------ minimisation pieces
 @pytest.mark.parametrize("dims,G,K,kind", [((24, 16, 1), 3, 1, "SMSM_GLOBAL"), ((24, 16, 1), 3, 1, "SMSM_LOCAL"), ((8, 8, 6), 2, 0, "SMSM_GLOBAL"),
                                            ((37, 21, 1), 1, 0, "SMSM_GLOBAL")])
