@@ -726,7 +726,7 @@ struct MdotArgs {
 };
 
 template <int NVMAX, int U>
-__global__ void __launch_bounds__(MSPK_THREADS) k_mdot(MdotArgs a, ReduceWs ws) {
+__global__ void __launch_bounds__(MSPK_THREADS, NVMAX > 16 ? 1 : 2) k_mdot(MdotArgs a, ReduceWs ws) {
   if (a.guard_it >= 0) {
     if (!a.ctl->active || a.ctl->it != a.guard_it) return;
     if (a.guard_refine && !a.ctl->refine) return;
@@ -781,11 +781,12 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_mdot(MdotArgs a, ReduceWs ws) 
   __shared__ double sm[32];
   __shared__ bool last;
   const int slot = 8 + g; // reduce slots 8.. are MDot groups
+  // partial sums: workspace rows 64 + g * NVMAX + v (192 rows in all; at most 64 + 24 + 23)
 #pragma unroll
   for (int v = 0; v < NVMAX; v++) {
     if (v < nv) {
       double bs = block_sum(acc[v], sm);
-      if (threadIdx.x == 0) ws.partial[(slot * 8 + v) * (long long)MSPK_MAX_PART + blockIdx.x] = bs;
+      if (threadIdx.x == 0) ws.partial[(64 + g * NVMAX + v) * (long long)MSPK_MAX_PART + blockIdx.x] = bs;
     }
   }
   if (threadIdx.x == 0) {
@@ -797,7 +798,7 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_mdot(MdotArgs a, ReduceWs ws) 
   if (last) {
     for (int v = 0; v < nv; v++) {
       double s = 0.0;
-      for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += __ldcg(ws.partial + (slot * 8 + v) * (long long)MSPK_MAX_PART + i);
+      for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += __ldcg(ws.partial + (64 + g * NVMAX + v) * (long long)MSPK_MAX_PART + i);
       double tot = block_sum(s, sm);
       // <w, v_j> = inv_j <w, vtilde_j>: the scale of the un-normalised basis vector is applied to the reduced value
       if (threadIdx.x == 0) a.h[v0 + v] = a.sign * (a.inv ? tot * a.inv[v0 + v] : tot);

@@ -40,7 +40,7 @@ rec(f"spmv {fmt.upper()} [CSR bytes]", ms, 12 * nnz + 4 * (n + 1) + 16 * n)
 rec(f"spmv {fmt.upper()} [own {width}-wide bytes]", ms, S.Engine.spmv_bytes_per_row(fmt, width) * n)
 ms = e.bench_kernel(5, iters=20)
 rec("spmv, input scaled on the fly", ms, 12 * nnz + 4 * (n + 1) + 16 * n)
-for nv in (1, 2, 4, 8, 9, 16, 24, 30):
+for nv in (1, 2, 4, 8, 9, 12, 16, 17, 20, 24, 25, 30):
     if nv > restart:
         continue
     rec(f"mdot nv={nv}", e.bench_kernel(1, nv, iters=10), 8 * n * (nv + 1))
