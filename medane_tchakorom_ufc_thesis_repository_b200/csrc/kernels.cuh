@@ -778,17 +778,28 @@ __global__ void __launch_bounds__(MSPK_THREADS, NVMAX > 16 ? 1 : 2) k_mdot(MdotA
     for (int v = 0; v < NVMAX; v++)
       if (v < nv) acc[v] = fma(Vg[v * a.ld + a.nb - 1], wl, acc[v]);
   }
-  __shared__ double sm[32];
+  // ---- block partials: warp sums of all vectors, ONE barrier, thread v adds the 8 warp sums of vector v in warp order
+  __shared__ double sm[(MSPK_THREADS / 32) * NVMAX];
   __shared__ bool last;
   const int slot = 8 + g; // reduce slots 8.. are MDot groups
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // partial sums: workspace rows 64 + g * NVMAX + v (192 rows in all; at most 64 + 24 + 23)
 #pragma unroll
   for (int v = 0; v < NVMAX; v++) {
     if (v < nv) {
-      double bs = block_sum(acc[v], sm);
-      if (threadIdx.x == 0) ws.partial[(64 + g * NVMAX + v) * (long long)MSPK_MAX_PART + blockIdx.x] = bs;
+      const double ws_ = warp_sum(acc[v]);
+      if (lane == 0) sm[wid * NVMAX + v] = ws_;
     }
   }
+  __syncthreads();
+  if (threadIdx.x < nv) {
+    double bs = 0.0;
+#pragma unroll
+    for (int w = 0; w < MSPK_THREADS / 32; w++) bs += sm[w * NVMAX + threadIdx.x];
+    ws.partial[(64 + g * NVMAX + threadIdx.x) * (long long)MSPK_MAX_PART + blockIdx.x] = bs;
+    __threadfence();
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     unsigned t = atomicAdd(ws.counter + slot, 1u);
@@ -796,12 +807,21 @@ __global__ void __launch_bounds__(MSPK_THREADS, NVMAX > 16 ? 1 : 2) k_mdot(MdotA
   }
   __syncthreads();
   if (last) {
-    for (int v = 0; v < nv; v++) {
-      double s = 0.0;
-      for (int i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += __ldcg(ws.partial + (64 + g * NVMAX + v) * (long long)MSPK_MAX_PART + i);
-      double tot = block_sum(s, sm);
+    // ---- last block to arrive: one warp per vector (all vectors in parallel), lane-strided sum in block order, then the
+    // shuffle tree — a fixed order, hence deterministic.  (The first version walked the vectors one after the other with two
+    // block barriers each: ~1.2 us per vector, 11 % of a 170 us launch at 8.4 M rows and 20 vectors.)
+    __threadfence();
+    for (int v = wid; v < nv; v += MSPK_THREADS / 32) {
+      const double *row = ws.partial + (64 + g * NVMAX + v) * (long long)MSPK_MAX_PART;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int i = lane;
+      for (; i + 96 < (int)gridDim.x; i += 128) {
+        s0 += __ldcg(row + i); s1 += __ldcg(row + i + 32); s2 += __ldcg(row + i + 64); s3 += __ldcg(row + i + 96);
+      }
+      for (; i < (int)gridDim.x; i += 32) s0 += __ldcg(row + i);
+      const double tot = warp_sum((s0 + s1) + (s2 + s3));
       // <w, v_j> = inv_j <w, vtilde_j>: the scale of the un-normalised basis vector is applied to the reduced value
-      if (threadIdx.x == 0) a.h[v0 + v] = a.sign * (a.inv ? tot * a.inv[v0 + v] : tot);
+      if (lane == 0) a.h[v0 + v] = a.sign * (a.inv ? tot * a.inv[v0 + v] : tot);
     }
     if (threadIdx.x == 0) ws.counter[slot] = 0;
   }
