@@ -490,6 +490,11 @@ static int op_normal_equations(msp_engine *e, int kind, int s, bool global, doub
 
 // small dense least squares on the host: stack nfac upper factors [U_k | c_k; 0 rho_k] and solve by
 // Householder QR.  This is the root of the TSQR tree (s <= 32: a few kflop).
+// Rank handling: a basis column that is numerically dependent on the ones before it (iterates identical to rounding —
+// this happens once a run has converged to machine precision) is dropped, alpha_k = 0, and does NOT consume a pivot
+// row: the next column is reflected at the same row, so what the dropped column's row still holds of the right-hand
+// side is minimised by the later columns and |diag[s]| stays the true residual norm of the returned alpha.  With no
+// dependent column the arithmetic is the plain Householder QR, operation for operation.
 static int tsqr_combine(int s, int nfac, const double *uall, double *alpha, double *resnorm) {
   const int nc = s + 1, rows = nfac * nc;
   std::vector<double> A((size_t)rows * nc, 0.0); // column-major rows x nc
@@ -497,33 +502,39 @@ static int tsqr_combine(int s, int nfac, const double *uall, double *alpha, doub
     for (int c = 0; c < nc; c++)
       for (int r = 0; r <= c; r++) A[(size_t)c * rows + f * nc + r] = uall[(size_t)f * nc * nc + (size_t)c * nc + r];
   std::vector<double> diag(nc, 0.0);
+  std::vector<int> prow(nc, -1); // pivot row of every column, -1 = dropped
+  int rk = 0;                    // next pivot row
+  double dmax_so_far = 0.0;
   for (int k = 0; k < nc; k++) {
     double *a = &A[(size_t)k * rows];
     double nrm = 0.0;
-    for (int r = k; r < rows; r++) nrm += a[r] * a[r];
+    for (int r = rk; r < rows; r++) nrm += a[r] * a[r];
     nrm = std::sqrt(nrm);
-    if (nrm == 0.0) { diag[k] = 0.0; continue; }
-    double beta = (a[k] >= 0.0) ? -nrm : nrm;
-    a[k] -= beta;
+    if (nrm == 0.0 || (k < s && nrm <= 1e-14 * dmax_so_far)) { diag[k] = 0.0; continue; }
+    double beta = (a[rk] >= 0.0) ? -nrm : nrm;
+    a[rk] -= beta;
     double vtv = 0.0;
-    for (int r = k; r < rows; r++) vtv += a[r] * a[r];
+    for (int r = rk; r < rows; r++) vtv += a[r] * a[r];
     for (int j = k + 1; j < nc; j++) {
       double *aj = &A[(size_t)j * rows];
       double d = 0.0;
-      for (int r = k; r < rows; r++) d += a[r] * aj[r];
+      for (int r = rk; r < rows; r++) d += a[r] * aj[r];
       d = 2.0 * d / vtv;
-      for (int r = k; r < rows; r++) aj[r] -= d * a[r];
+      for (int r = rk; r < rows; r++) aj[r] -= d * a[r];
     }
     diag[k] = beta;
+    prow[k] = rk++;
+    dmax_so_far = std::max(dmax_so_far, std::fabs(beta));
   }
-  // back substitution on the leading s x s block against column s
+  // back substitution on the pivot rows of the leading s columns against column s
   const double *cvec = &A[(size_t)s * rows];
   double dmax = 0.0;
   for (int k = 0; k < s; k++) dmax = std::max(dmax, std::fabs(diag[k]));
   for (int k = s - 1; k >= 0; k--) {
-    double t = cvec[k];
-    for (int j = k + 1; j < s; j++) t -= A[(size_t)j * rows + k] * alpha[j];
-    // numerically dependent basis vector (iterates identical to rounding): drop it
+    if (prow[k] < 0) { alpha[k] = 0.0; continue; }
+    double t = cvec[prow[k]];
+    for (int j = k + 1; j < s; j++) t -= A[(size_t)j * rows + prow[k]] * alpha[j];
+    // numerically dependent basis vector that still got a pivot (smaller than 1e-14 of a LATER column): drop it
     alpha[k] = (std::fabs(diag[k]) > 1e-14 * dmax) ? t / diag[k] : 0.0;
   }
   if (resnorm) *resnorm = std::fabs(diag[s]);

@@ -121,3 +121,32 @@ def test_bench_gpu_arm_refuses_to_run_without_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True,
                          text=True, timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_tsqr_root_is_exact_least_squares():
+    """msp_tsqr_combine is host arithmetic (the root of the TSQR tree: Householder QR of the stacked (s+1)x(s+1) factors), so
+    it is checked here without a GPU: factors made by numpy's QR of random row blocks [R_K | b_K] must give the least-squares
+    solution and residual norm of the stacked system, for every basis size the drivers use and for 1..8 blocks."""
+    import numpy as np
+    from medane_tchakorom_ufc_thesis_repository_b200 import solver as S
+    rng = np.random.default_rng(3)
+    for s in (1, 3, 4, 5, 10, 20):
+        for G in (1, 2, 4, 8):
+            rows = 3 * (s + 1)
+            blocks = [rng.standard_normal((rows, s + 1)) for _ in range(G)]
+            factors = []
+            for B in blocks:
+                U = np.linalg.qr(B, mode="r")                       # (s+1) x (s+1) upper factor of [R_K | b_K]
+                factors.append(np.asfortranarray(U).reshape(-1, order="F"))  # column-major, as op_local_qr hands it over
+            alpha, rn = S.tsqr_combine(s, factors)
+            A = np.vstack(blocks)
+            ref, res, *_ = np.linalg.lstsq(A[:, :s], A[:, s], rcond=None)
+            assert np.allclose(alpha, ref, rtol=1e-10, atol=1e-12), (s, G)
+            assert abs(rn - np.sqrt(res[0])) <= 1e-10 * np.sqrt(res[0])
+    # a numerically dependent basis vector (two identical iterates) is dropped, not divided by ~0
+    B = rng.standard_normal((12, 4))
+    B[:, 1] = B[:, 0]
+    U = np.linalg.qr(B, mode="r")
+    alpha, rn = S.tsqr_combine(3, [np.asfortranarray(U).reshape(-1, order="F")])
+    assert np.all(np.isfinite(alpha)) and np.isfinite(rn)
+    assert abs(np.linalg.norm(B[:, :3] @ alpha - B[:, 3]) - rn) <= 1e-8 * max(rn, 1.0)

@@ -196,3 +196,22 @@ def test_async_four_blocks_chain_terminates(oracle):
     assert r["rc"] == 0 and all(i > 0 for i in r["outer_its_block"]) and r["final_residual"] <= 1e-3 * r["norm0"]
     r = oracle.solve("AMAM_GLOBAL", 8, 8, p=8, nblocks=4, s=3, rtol=1e-4, inner=inner, periods=[2, 1, 1, 1], max_outer=6000)
     assert r["rc"] == 0 and r["final_residual"] <= 1e-3 * r["norm0"]
+
+
+def test_sync_run_fixtures_are_what_the_oracle_produces(oracle):
+    """tests/golden/oracle_sync_runs.json (made by make_oracle_sync_runs.py) is what the GPU parity tests compare against:
+    re-run a subset here so that a change of the oracle cannot silently move the bar."""
+    with open(os.path.join(GOLD, "oracle_sync_runs.json")) as f:
+        runs = json.load(f)["runs"]
+    checked = 0
+    for g in runs:
+        if g["outer_its"] > 60:      # keep the CPU suite short: the long SM sweeps are re-run by the GPU tests anyway
+            continue
+        r = oracle.solve(g["alg"], g["m"], g["n"], p=g.get("p", 1), nblocks=g["nblocks"], s=g["s"], rtol=g["rtol"], inner=g["inner"],
+                         max_outer=3000)
+        assert r["outer_its"] == g["outer_its"], (g["alg"], g["m"], g["n"])
+        assert r["inner_its_total"] == g["inner_its_total"]
+        assert abs(r["norm0"] - g["norm0"]) <= 1e-14 * g["norm0"]
+        assert abs(r["final_residual"] - g["final_residual"]) <= 1e-9 * g["final_residual"]
+        checked += 1
+    assert checked >= 10
