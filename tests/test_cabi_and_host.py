@@ -150,3 +150,54 @@ def test_tsqr_root_is_exact_least_squares():
     alpha, rn = S.tsqr_combine(3, [np.asfortranarray(U).reshape(-1, order="F")])
     assert np.all(np.isfinite(alpha)) and np.isfinite(rn)
     assert abs(np.linalg.norm(B[:, :3] @ alpha - B[:, 3]) - rn) <= 1e-8 * max(rn, 1.0)
+
+
+def test_isolve_accepts_the_reference_option_spellings(tmp_path):
+    """iSolve is the reference's launcher interface (reference iSolve:94-115, :60-200): its own option spellings must be
+    accepted and end up, like there, as -inner_ksp_* / -outer_ksp_* options of the solver binary.  The binary is replaced by
+    a stub that prints its arguments (MSOLVE=...), so nothing here needs a GPU."""
+    stub = tmp_path / "msolve_stub"
+    stub.write_text("#!/bin/sh\necho \"STUB $@\"\n")
+    stub.chmod(0o755)
+    env = dict(os.environ, MSOLVE=str(stub))
+    isolve = os.path.join(ROOT, "iSolve")
+
+    def run(*args):
+        return subprocess.run([isolve, *args], capture_output=True, text=True, env=env, timeout=60)
+
+    out = run("--alg", "SMSM_GLOBAL", "--np", "2", "--npb", "1", "--m", "512", "--n", "256", "--s", "5", "--rtol", "1e-6",
+              "--inner-ksp", "gmres", "--inner-rtol", "1e-10", "--inner-max-iters", "20", "--inner-pc-type", "none",
+              "--outer-ksp", "lsqr", "--outer-rtol", "1e-15", "--outer-max-iters", "70", "--outer-pc-type", "none",
+              "--other-petsc-options", "-log_view -minimizer lsqr")
+    assert out.returncode == 0, out.stderr
+    assert "Program : synchronous-multisplitting-synchronous-minimization-global" in out.stdout
+    assert "Mesh size : 512 x 256" in out.stdout and "OUTER solver max iterations : 70" in out.stdout
+    assert "RUNNING COMMAND:" in out.stdout
+    stub_line = [l for l in out.stdout.splitlines() if l.startswith("STUB ")][0].split()[1:]
+    opts = {stub_line[i]: stub_line[i + 1] for i in range(len(stub_line) - 1) if stub_line[i].startswith("-")}
+    assert opts["-alg"] == "SMSM_GLOBAL" and opts["-nblocks"] == "2" and opts["-m"] == "512" and opts["-n"] == "256"
+    assert opts["-s"] == "5" and opts["-rtol"] == "1e-6"
+    assert opts["-inner_ksp_type"] == "gmres" and opts["-inner_ksp_rtol"] == "1e-10" and opts["-inner_ksp_max_it"] == "20"
+    assert opts["-inner_pc_type"] == "none"
+    assert opts["-outer_ksp_type"] == "lsqr" and opts["-outer_ksp_rtol"] == "1e-15" and opts["-outer_ksp_max_it"] == "70"
+    assert opts["-minimizer"] == "lsqr" and "-log_view" in stub_line
+    assert "-min_convergence_count" not in opts                       # synchronous binaries do not get it (iSolve:362)
+    # defaults of config/default_run_variables: AM, 2 processes, 1024 x 1024, s = 4, rtol 1e-3, inner gmres 20 / 1e-3
+    out = run("--convergence_count_min", "7")
+    stub_line = [l for l in out.stdout.splitlines() if l.startswith("STUB ")][0].split()[1:]
+    opts = {stub_line[i]: stub_line[i + 1] for i in range(len(stub_line) - 1) if stub_line[i].startswith("-")}
+    assert opts["-alg"] == "AM" and opts["-m"] == "1024" and opts["-n"] == "1024" and opts["-rtol"] == "1e-3"
+    assert opts["-min_convergence_count"] == "7" and opts["-inner_ksp_max_it"] == "20" and "-s" not in opts
+    assert "-outer_ksp_type" not in opts
+    # np / npb that do not give whole blocks: the reference prints this and exits 0 (iSolve:332-338)
+    out = run("--np", "3", "--npb", "2")
+    assert out.returncode == 0 and "are not matching" in out.stdout and "STUB" not in out.stdout
+    # several blocks (generalisation), stand-alone GMRES takes un-prefixed options, unknown things are refused
+    out = run("--alg", "SM", "--np", "8", "--npb", "1")
+    assert "-nblocks 8" in out.stdout
+    out = run("--alg", "GMRES", "--inner-max-iters", "500")
+    assert "-ksp_max_it 500" in out.stdout and "-inner_ksp_max_it" not in out.stdout and "-nblocks 1" in out.stdout
+    assert run("--alg", "SMSM").returncode == 2
+    assert run("--inner-ksp", "preonly").returncode == 2
+    assert run("--bogus", "1").returncode == 2
+    assert run("--m").returncode == 1
