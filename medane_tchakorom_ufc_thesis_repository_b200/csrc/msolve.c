@@ -104,6 +104,10 @@ static int alg_from_name(const char *s) {
     {"GMRES", MSP_ALG_GMRES}, {"gmres_solution", MSP_ALG_GMRES},
     {"AM", MSP_ALG_AM}, {"asynchronous-multisplitting_prime", MSP_ALG_AM}, {"asynchronous-multisplitting", MSP_ALG_AM},
     {"AMAM_GLOBAL", MSP_ALG_AMAM_GLOBAL}, {"asynchronous-multisplitting-asynchronous-minimization-global_prime", MSP_ALG_AMAM_GLOBAL},
+    /* iSolve:50-56 names the asynchronous binaries without the _prime suffix the makefile gives them (makefile:135,148) */
+    {"asynchronous-multisplitting-asynchronous-minimization-global", MSP_ALG_AMAM_GLOBAL},
+    {"asynchronous-multisplitting-asynchronous-minimization-semi-local", MSP_ALG_AMAM_SEMI_LOCAL},
+    {"asynchronous-multisplitting-asynchronous-minimization-local", MSP_ALG_AMAM_LOCAL},
     /* iSolve:56 maps AMAM_SEMI_LOCAL to the *local* binary; dispatched correctly here */
     {"AMAM_SEMI_LOCAL", MSP_ALG_AMAM_SEMI_LOCAL}, {"asynchronous-multisplitting-asynchronous-minimization-semi-local_prime", MSP_ALG_AMAM_SEMI_LOCAL},
     {"AMAM_LOCAL", MSP_ALG_AMAM_LOCAL}, {"asynchronous-multisplitting-asynchronous-minimization-local_prime", MSP_ALG_AMAM_LOCAL},

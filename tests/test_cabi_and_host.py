@@ -170,7 +170,7 @@ def test_isolve_accepts_the_reference_option_spellings(tmp_path):
               "--outer-ksp", "lsqr", "--outer-rtol", "1e-15", "--outer-max-iters", "70", "--outer-pc-type", "none",
               "--other-petsc-options", "-log_view -minimizer lsqr")
     assert out.returncode == 0, out.stderr
-    assert "Program : synchronous-multisplitting-synchronous-minimization-global" in out.stdout
+    assert "Program : Synchronous Multisplitting & Synchronous Minimization (GLOBAL MINIMIZATION)" in out.stdout
     assert "Mesh size : 512 x 256" in out.stdout and "OUTER solver max iterations : 70" in out.stdout
     assert "RUNNING COMMAND:" in out.stdout
     stub_line = [l for l in out.stdout.splitlines() if l.startswith("STUB ")][0].split()[1:]
