@@ -215,3 +215,47 @@ def test_sync_run_fixtures_are_what_the_oracle_produces(oracle):
         assert abs(r["final_residual"] - g["final_residual"]) <= 1e-9 * g["final_residual"]
         checked += 1
     assert checked >= 10
+
+
+def test_assembly_properties_random_shapes(oracle):
+    """Property test over random grid shapes and block counts (hypothesis): the strips stacked over the blocks are the
+    symmetric stencil matrix with the closed-form row sums, and — the precondition of the engine's coded-DIA view —
+    every diagonal of a strip holds ONE value wherever it is present."""
+    import scipy.sparse as sp
+    from hypothesis import given, settings, strategies as st
+
+    def check(strips, ntot, expect_rowsum, diag_value):
+        A = sp.vstack([sp.csr_matrix((va, ci, rp), shape=(len(rp) - 1, ntot)) for rp, ci, va in strips]).tocsr()
+        assert A.shape == (ntot, ntot)
+        assert abs(A - A.T).sum() == 0
+        assert np.array_equal(np.asarray(A.sum(axis=1)).ravel(), expect_rowsum)
+        assert np.all(A.diagonal() == diag_value)
+        coo = A.tocoo()
+        for off in np.unique(coo.col - coo.row):
+            vals = coo.data[(coo.col - coo.row) == off]
+            assert np.all(vals == vals[0])       # one constant per diagonal
+        for rp, ci, va in strips:
+            for r in range(len(rp) - 1):
+                assert np.all(np.diff(ci[rp[r]:rp[r + 1]]) > 0)   # sorted columns, as MatAssembly leaves them
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(1, 4), st.integers(1, 6), st.integers(1, 12))
+    def two_d(G, lines_per_block, n):
+        m = G * lines_per_block
+        idx = np.arange(m * n)
+        i, j = idx // n, idx % n
+        # one unit per missing neighbour (a 1-wide grid misses both column neighbours)
+        rowsum = (i == 0).astype(float) + (i == m - 1) + (j == 0) + (j == n - 1)
+        check([oracle.poisson2d(m, n, k, G) for k in range(G)], m * n, rowsum, 4.0)
+
+    @settings(max_examples=15, deadline=None)
+    @given(st.integers(1, 3), st.integers(1, 3), st.integers(1, 6), st.integers(1, 6))
+    def three_d(G, planes_per_block, nx, ny):
+        nz = G * planes_per_block
+        idx = np.arange(nx * ny * nz)
+        i, j, k = idx % nx, (idx // nx) % ny, idx // (nx * ny)
+        rowsum = (i == 0).astype(float) + (i == nx - 1) + (j == 0) + (j == ny - 1) + (k == 0) + (k == nz - 1)
+        check([oracle.poisson3d(nx, ny, nz, b, G) for b in range(G)], nx * ny * nz, rowsum, 6.0)
+
+    two_d()
+    three_d()
