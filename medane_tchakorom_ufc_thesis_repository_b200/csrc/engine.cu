@@ -294,7 +294,7 @@ static void launch_mdot(msp_engine *e, int nv, const double *V, long long ldv, c
   MdotArgs a{};
   a.nb = e->nb; a.nv = nv; a.ld = ldv; a.V = V; a.w = w; a.h = h; a.sign = sign; a.ctl = e->ctl; a.inv = inv;
   a.guard_it = guard_it; a.guard_refine = guard_refine;
-  static const int gmax = getenv("MSPLIT_MDOT_GROUP") ? atoi(getenv("MSPLIT_MDOT_GROUP")) : 24; // vectors per y-group (measured at 67 M rows: 8 -> 6.6-6.9 TB/s for nv > 8, 24 -> 7.0-7.3)
+  static const int gmax = getenv("MSPLIT_MDOT_GROUP") ? std::min(24, std::max(1, atoi(getenv("MSPLIT_MDOT_GROUP")))) : 24; // vectors per y-group (measured at 67 M rows: 8 -> 6.6-6.9 TB/s for nv > 8, 24 -> 7.0-7.3)
   int ngroups = (nv + gmax - 1) / gmax;
   a.per_group = (nv + ngroups - 1) / ngroups;
   ngroups = (nv + a.per_group - 1) / a.per_group;
