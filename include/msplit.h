@@ -86,13 +86,22 @@ typedef struct {
   /* minimiser (outer_solver_norm_equation utils.c:1061-1103): 0 = exact least squares by TSQR (default),
    * 1 = PETSc-faithful LSQR on R with zero initial guess and the initial-residual-norm test, as every shipped
    * command line selects (-outer{K}_ksp_type lsqr -outer{K}_ksp_max_it 40..200 -outer{K}_ksp_rtol 1e-14..1e-50),
-   * 2 = normal equations on the Gram matrix R'R (the reference's `outer_solver`, utils.c:972-996), s <= 8 */
+   * 2 = normal equations on the Gram matrix R'R solved by Cholesky (the reference's `outer_solver`, utils.c:972-996), s <= 8,
+   * 3 = the same Gram system solved by PETSc's CG (`outer_solver` with -outer_ksp_type cg, config/default_run_variables), s <= 8,
+   * 4 = CGNE on R without forming R'R (`outer_solver_cgne`, utils.c:1020-1043) */
   int outer_type;
   int outer_max_it;
   double outer_rtol, outer_abstol;
   /* async emulation in one process: block K runs a step at tick t iff t % period[K] == 0 */
   int period[MSP_MAX_BLOCKS];
+  /* wall-clock cap of the outer loop in seconds (reference: the `timeout -k 5s 3600` wrapper of
+   * running_bulk_test_local:3-7); 0 = none.  Synchronous variants agree on it collectively (one extra 1-double
+   * allreduce per outer iteration, only when the cap is set), asynchronous blocks stop on their own clock. */
+  double max_seconds;
 } msp_solve_opts;
+
+/* why the outer loop ended (msp_result.stop_reason) */
+enum { MSP_STOP_CONVERGED = 0, MSP_STOP_MAX_OUTER = 1, MSP_STOP_MAX_SECONDS = 2 };
 
 typedef struct {
   int outer_its;              /* number_of_iterations printed by utils.c:703-729 */
@@ -115,6 +124,8 @@ typedef struct {
    * and in the exchange + minimisation + convergence test ("O_Solver stage") */
   double stage_inner_s, stage_outer_s;
   int64_t outer_solver_its;   /* LSQR iterations summed over the outer iterations (0 with TSQR) */
+  int hist_dropped;           /* history entries that did not fit hist[4096] (the first 4096 are kept) */
+  int stop_reason;            /* MSP_STOP_* */
 } msp_result;
 
 int msp_version(void);
@@ -171,6 +182,30 @@ int msp_minimize_local_qr(msp_engine *e, int kind, double *u_aug);
 int msp_apply_alpha(msp_engine *e, int kind, const double *alpha);
 /* small stacked least squares: nfac factors u_aug[(s+1)^2] -> alpha[s], ||b - R alpha|| (outer_solver_norm_equation utils.c:1061-1078) */
 int msp_tsqr_combine(int s, int nfac, const double *u_aug_all, double *alpha, double *resnorm);
+
+/* ---- the fine-grained exchange and minimiser a reference main() drives itself (include/comm.h, include/utils.h) ---- */
+int msp_get_solution(msp_engine *e, double *x);            /* = msp_get_x: the block's slice of the iterate */
+int msp_split_blocks(msp_engine *e, int which, int32_t *rowptr, int32_t *colidx, double *val); /* divideSubDomainIntoBlockMatrices utils.c:450-478 (= msp_get_csr) */
+int msp_compute_rhs_ones(msp_engine *e);                   /* computeTheRightHandSideWithInitialGuess utils.c:623-650: b_K = A_K,: 1, rhs_K = b_K, halos 0 */
+int msp_residual_norm(msp_engine *e, double *nrm);         /* computeFinalResidualNorm utils.c:575-595: sqrt(sum_K ||b_K - A_K,: x||^2), collective */
+/* wire two engines of ONE process as neighbours (side 0: `neighbour` is block K-1, side 1: block K+1); msp_group_create and
+ * msp_comm_connect do the same for a whole group / across processes */
+int msp_connect_local(msp_engine *e, int side, msp_engine *neighbour);
+/* comm_sync_send_and_receive comm.c:126-141: store my boundary layers into the neighbours' receive windows (P2P), wait until
+ * every block has done so, copy the received layers into the private halos.  Collective: one caller per block (threads of a
+ * group, or one process per GPU). */
+int msp_exchange_sync(msp_engine *e);
+/* comm_async_test_and_send_prime comm.c:531-554: store the layers, then release the header {seq, PhaseTag, iteration}.
+ * comm_async_probe_and_receive_prime comm.c:455-529: take the newest header of each neighbour, let receive_data_dependency
+ * (conv_detection_prime.c:603-633) decide, copy the layer; accepted[side] = 1 if a layer was taken.  Never block. */
+int msp_async_reset(msp_engine *e);                        /* state of a new asynchronous run (…multisplitting_prime.c:280-315) */
+int msp_exchange_async_publish(msp_engine *e, int iteration);
+int msp_exchange_async_poll(msp_engine *e, int *accepted /* [2], may be null */);
+/* outer_solver_norm_equation[_modify] utils.c:1061-1103 and the rest of the outer-solver menu (outer_solver utils.c:972-996,
+ * outer_solver_cgne utils.c:1020-1043): least squares on R = A S (msp_spmm_AS) against b_K (rhs_K for LOCAL), then x = S alpha.
+ * kind: MSP_ALG_SMSM_GLOBAL (collective: one problem over all blocks) | _SEMI_LOCAL | _LOCAL.
+ * outer_type: 0 exact LS (TSQR), 1 LSQR, 2 normal equations + Cholesky, 3 CG on the normal equations, 4 CGNE. */
+int msp_minimize(msp_engine *e, int kind, int outer_type, int outer_max_it, double outer_rtol, double *alpha, double *resnorm);
 
 /* raw kernels on host data, for parity tests and micro-benchmarks */
 int msp_op_spmv(msp_engine *e, int which, const double *x, const double *halo_lo, const double *halo_hi, double *y);

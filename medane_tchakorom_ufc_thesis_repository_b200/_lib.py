@@ -40,6 +40,7 @@ class SolveOpts(C.Structure):
         ("alg", C.c_int), ("s", C.c_int), ("rtol", C.c_double), ("inner", KspOpts), ("max_outer", C.c_int),
         ("record_history", C.c_int), ("profile", C.c_int), ("outer_type", C.c_int), ("outer_max_it", C.c_int),
         ("outer_rtol", C.c_double), ("outer_abstol", C.c_double), ("period", C.c_int * MAX_BLOCKS),
+        ("max_seconds", C.c_double),
     ]
 
 
@@ -53,6 +54,7 @@ class Result(C.Structure):
         ("b_spmv", C.c_double), ("b_mdot", C.c_double), ("b_maxpy", C.c_double), ("b_other", C.c_double),
         ("n_spmv", C.c_int64), ("n_mdot", C.c_int64), ("n_maxpy", C.c_int64), ("n_other", C.c_int64),
         ("stage_inner_s", C.c_double), ("stage_outer_s", C.c_double), ("outer_solver_its", C.c_int64),
+        ("hist_dropped", C.c_int), ("stop_reason", C.c_int),
     ]
 
     def as_dict(self):
@@ -63,6 +65,7 @@ class Result(C.Structure):
             "gmres_rnorm": self.gmres_rnorm, "hist": np.array(self.hist[: self.hist_len]),
             "kernel_launches": self.kernel_launches, "stage_inner_s": self.stage_inner_s,
             "stage_outer_s": self.stage_outer_s, "outer_solver_its": self.outer_solver_its,
+            "hist_dropped": self.hist_dropped, "stop_reason": self.stop_reason,
             "prof": {c: {"ms": getattr(self, f"t_{c}_ms"), "bytes": getattr(self, f"b_{c}"), "launches": getattr(self, f"n_{c}")}
                      for c in ("spmv", "mdot", "maxpy", "other")},
         }
@@ -78,7 +81,9 @@ EXPORTS = [
     "msp_minimize_local_qr", "msp_apply_alpha", "msp_tsqr_combine", "msp_op_spmv", "msp_op_mdot", "msp_op_maxpy",
     "msp_bench_kernel", "msp_gmres_solve", "msp_group_create", "msp_group_destroy", "msp_group_engine",
     "msp_group_solve", "msp_comm_unique_id", "msp_comm_init", "msp_comm_export", "msp_comm_connect", "msp_comm_connect_block", "msp_solve",
-    "msp_conv_detect_step",
+    "msp_conv_detect_step", "msp_get_solution", "msp_split_blocks", "msp_compute_rhs_ones", "msp_residual_norm",
+    "msp_connect_local", "msp_exchange_sync", "msp_async_reset", "msp_exchange_async_publish", "msp_exchange_async_poll",
+    "msp_minimize",
 ]
 
 _lib = None
@@ -145,6 +150,16 @@ def lib() -> C.CDLL:
     L.msp_comm_connect_block.argtypes = [vp, C.c_int, C.c_char_p]
     L.msp_solve.argtypes = [vp, C.POINTER(SolveOpts), C.POINTER(Result)]
     L.msp_conv_detect_step.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.msp_get_solution.argtypes = [vp, f64p]
+    L.msp_split_blocks.argtypes = [vp, C.c_int, i32p, i32p, f64p]
+    L.msp_compute_rhs_ones.argtypes = [vp]
+    L.msp_residual_norm.argtypes = [vp, C.POINTER(C.c_double)]
+    L.msp_connect_local.argtypes = [vp, C.c_int, vp]
+    L.msp_exchange_sync.argtypes = [vp]
+    L.msp_async_reset.argtypes = [vp]
+    L.msp_exchange_async_publish.argtypes = [vp, C.c_int]
+    L.msp_exchange_async_poll.argtypes = [vp, C.POINTER(C.c_int)]
+    L.msp_minimize.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, f64p, C.POINTER(C.c_double)]
     _lib = L
     return L
 

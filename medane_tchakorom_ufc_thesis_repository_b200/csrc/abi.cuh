@@ -219,6 +219,101 @@ int msp_tsqr_combine(int s, int nfac, const double *u_aug_all, double *alpha, do
   return tsqr_combine(s, nfac, u_aug_all, alpha, resnorm);
 }
 
+// ---- the §8(b) export list under its own names ----
+int msp_get_solution(msp_engine *e, double *x) { return msp_get_x(e, x); }
+int msp_split_blocks(msp_engine *e, int which, int32_t *rowptr, int32_t *colidx, double *val) { return msp_get_csr(e, which, rowptr, colidx, val); }
+int msp_compute_rhs_ones(msp_engine *e) {
+  if (!e) MSP_FAIL("null engine");
+  cudaSetDevice(e->device);
+  return op_compute_rhs_ones(e);
+}
+int msp_residual_norm(msp_engine *e, double *nrm) {
+  // computeFinalResidualNorm utils.c:575-595: sqrt(sum over blocks of ||b_K - A_K,: x||^2), collective
+  if (!e || !nrm) MSP_FAIL("null argument");
+  cudaSetDevice(e->device);
+  RC(op_resid_sumsq(e, true, 0));
+  RC(allreduce_host(e, 0, 1));
+  *nrm = std::sqrt(e->hsc[0]);
+  return 0;
+}
+int msp_exchange_sync(msp_engine *e) {
+  // comm_sync_send_and_receive comm.c:126-141: my boundary layers into the neighbours' windows, wait for theirs, collect
+  if (!e) MSP_FAIL("null engine");
+  cudaSetDevice(e->device);
+  for (int side = 0; side < 2; side++)
+    if (e->has_nb[side] && !e->peer[side].base) MSP_FAIL("neighbour window not connected");
+  RC(op_publish_boundary(e));
+  RC(exchange_sync(e));
+  CK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+int msp_exchange_async_publish(msp_engine *e, int iteration) {
+  // comm_async_test_and_send_prime comm.c:531-554
+  if (!e) MSP_FAIL("null engine");
+  cudaSetDevice(e->device);
+  RC(async_publish(e, iteration));
+  CK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+int msp_exchange_async_poll(msp_engine *e, int *accepted /* [2] or null */) {
+  // comm_async_probe_and_receive_prime comm.c:455-529 + receive_data_dependency conv_detection_prime.c:603-633
+  if (!e) MSP_FAIL("null engine");
+  cudaSetDevice(e->device);
+  RC(async_probe(e));
+  ProbeDecision hd[2];
+  CK(cudaMemcpyAsync(hd, e->dec, sizeof(hd), cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  if (accepted) for (int side = 0; side < 2; side++) accepted[side] = e->has_nb[side] ? hd[side].copy : 0;
+  return 0;
+}
+int msp_async_reset(msp_engine *e) {
+  // start of an asynchronous run: convergence-detection state, mailboxes and header counters (…multisplitting_prime.c:280-315)
+  if (!e) MSP_FAIL("null engine");
+  cudaSetDevice(e->device);
+  k_cd_init<<<1, 32, 0, e->st>>>(e->cd, e->prob.block, e->prob.nblocks, e->win.mailbox(), e->peer[0].base ? e->peer[0].mailbox() : nullptr,
+                                 e->peer[1].base ? e->peer[1].mailbox() : nullptr, e->win.hdr(0), e->win.hdr(1), e->aint);
+  e->launches++;
+  CK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+int msp_connect_local(msp_engine *e, int side, msp_engine *neighbour) {
+  // both engines live in this process: the neighbour's receive window is addressed directly (peer access when on another GPU)
+  if (!e || !neighbour || side < 0 || side > 1) MSP_FAIL("bad argument");
+  if (!e->has_nb[side]) MSP_FAIL("no neighbour on that side");
+  const int want = side == 0 ? e->prob.block - 1 : e->prob.block + 1;
+  if (neighbour->prob.block != want || neighbour->prob.nblocks != e->prob.nblocks || neighbour->H != e->H) MSP_FAIL("that engine is not the neighbour block of this side");
+  cudaSetDevice(e->device);
+  if (neighbour->device != e->device) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, e->device, neighbour->device);
+    if (!can) MSP_FAIL("peer access between the two GPUs is not available");
+    cudaError_t er = cudaDeviceEnablePeerAccess(neighbour->device, 0);
+    if (er != cudaSuccess && er != cudaErrorPeerAccessAlreadyEnabled) MSP_FAIL("cudaDeviceEnablePeerAccess failed");
+    cudaGetLastError();
+  }
+  e->peer[side] = neighbour->win; e->peer_ipc[side] = false;
+  e->peer_any[want] = neighbour->win; e->peer_any_ipc[want] = false;
+  return 0;
+}
+int msp_minimize(msp_engine *e, int kind, int outer_type, int outer_max_it, double outer_rtol, double *alpha, double *resnorm) {
+  // outer_solver_norm_equation[_modify] utils.c:1061-1103 (+ the LSQR / CG / CGNE menu, utils.c:972-1043) on R = A S
+  // computed by msp_spmm_AS: least squares, then x = S alpha.  kind GLOBAL is collective over the blocks.
+  if (!e || !alpha) MSP_FAIL("null argument");
+  cudaSetDevice(e->device);
+  int alg = kind;
+  if (kind == MSP_ALG_AMAM_GLOBAL) alg = MSP_ALG_SMSM_GLOBAL;
+  else if (kind == MSP_ALG_AMAM_SEMI_LOCAL) alg = MSP_ALG_SMSM_SEMI_LOCAL;
+  else if (kind == MSP_ALG_AMAM_LOCAL) alg = MSP_ALG_SMSM_LOCAL;
+  if (alg != MSP_ALG_SMSM_GLOBAL && alg != MSP_ALG_SMSM_SEMI_LOCAL && alg != MSP_ALG_SMSM_LOCAL) MSP_FAIL("kind must be a GLOBAL, SEMI_LOCAL or LOCAL minimisation");
+  if (e->smax < 1) MSP_FAIL("engine was created without a minimisation basis (s = 0)");
+  const MinimizeOpts mo{outer_type, outer_max_it > 0 ? outer_max_it : 100, outer_rtol > 0 ? outer_rtol : 1e-15, 1e-100};
+  double norm = 0.0;
+  RC(op_minimize(e, alg, e->smax, mo, alpha, &norm, nullptr));
+  CK(cudaStreamSynchronize(e->st));
+  if (resnorm) *resnorm = norm;
+  return 0;
+}
+
 // ---- raw kernels on host data (parity tests) ----
 int msp_op_spmv(msp_engine *e, int which, const double *x, const double *halo_lo, const double *halo_hi, double *y) {
   if (!e || !x || !y) MSP_FAIL("null argument");
@@ -343,15 +438,15 @@ int msp_group_solve(msp_group *g, const msp_solve_opts *o, msp_result *res) {
   std::vector<int> rcs(g->G, 0);
   std::vector<std::string> errs(g->G);
   std::vector<std::thread> th;
+  g->sh->reset();
   for (int k = 0; k < g->G; k++)
     th.emplace_back([&, k] {
       cudaSetDevice(g->eng[k]->device);
       rcs[k] = engine_solve_sync(g->eng[k], o, &res[k]);
-      if (rcs[k]) errs[k] = g_err;
+      if (rcs[k]) { errs[k] = g_err; g->sh->abort(); } // wake the blocks waiting for this one in a collective
     });
   for (auto &t : th) t.join();
-  for (int k = 0; k < g->G; k++) if (rcs[k]) { g_err = errs[k]; return rcs[k]; }
-  return 0;
+  return group_first_error(rcs, errs);
 }
 
 // ---- one process per GPU ----

@@ -25,12 +25,25 @@ struct LocalShared {
   long long gen = 0;
   std::vector<std::vector<double>> slot;
   std::vector<double> result;
+  bool aborted = false; // a block thread left its solve with an error: nobody may wait for it any more
   explicit LocalShared(int n_) : n(n_), slot(n_), result(0) {}
-  void wait_all() {
+  // false = the group was aborted (another block failed); the caller returns an error instead of waiting forever
+  bool wait_all() {
     std::unique_lock<std::mutex> lk(mu);
+    if (aborted) return false;
     long long g = gen;
     if (++arrived == n) { arrived = 0; gen++; cv.notify_all(); }
-    else cv.wait(lk, [&] { return gen != g; });
+    else cv.wait(lk, [&] { return gen != g || aborted; });
+    return !aborted;
+  }
+  void abort() {
+    std::lock_guard<std::mutex> lk(mu);
+    aborted = true;
+    cv.notify_all();
+  }
+  void reset() { // before a group solve starts its block threads
+    std::lock_guard<std::mutex> lk(mu);
+    aborted = false; arrived = 0;
   }
 };
 struct LocalComm : Comm {
@@ -42,20 +55,20 @@ struct LocalComm : Comm {
     CK(cudaMemcpyAsync(host.data(), dbuf, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     sh->slot[rank] = host;
-    sh->wait_all();
+    if (!sh->wait_all()) MSP_FAIL("group aborted: another block failed");
     for (int i = 0; i < n; i++) {
       double s = 0.0;
       for (int r = 0; r < nranks; r++) s += sh->slot[r][i]; // rank order: identical on every rank
       host[i] = s;
     }
-    sh->wait_all();
+    if (!sh->wait_all()) MSP_FAIL("group aborted: another block failed");
     CK(cudaMemcpyAsync(dbuf, host.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
     return 0;
   }
   int barrier(cudaStream_t st) override {
     CK(cudaStreamSynchronize(st));
-    sh->wait_all();
+    if (!sh->wait_all()) MSP_FAIL("group aborted: another block failed");
     return 0;
   }
 };

@@ -19,6 +19,68 @@ static int allreduce_host(msp_engine *e, int first, int n) {
   return read_scalars(e, first, n);
 }
 
+// outer_solver_norm_equation[_modify] utils.c:1061-1103 on one block: least squares on (R, rhs) with the selected
+// minimiser, then x = S alpha on the own rows and the stored neighbour layers.  `global`: one least-squares problem over
+// all blocks (collective: every block must call), otherwise block-local.  Returns alpha (host), the residual norm
+// ||rhs - R alpha|| where the minimiser provides one (TSQR global / LSQR / normal equations; 0 otherwise).
+struct MinimizeOpts { int outer_type, max_it; double rtol, abstol; };
+static int op_minimize(msp_engine *e, int alg, int s, const MinimizeOpts &mo, double *alpha, double *norm_out, int *lits_out) {
+  const int G = e->prob.nblocks;
+  const bool global = (alg == MSP_ALG_SMSM_GLOBAL);
+  double norm = 0.0;
+  int lits = 0;
+  if (mo.outer_type == 1) {
+    RC(op_lsqr(e, alg, s, global, mo.max_it, mo.rtol, mo.abstol, alpha, &norm, &lits));
+  } else if (mo.outer_type == 2) {
+    RC(op_normal_equations(e, alg, s, global, alpha, &norm));
+  } else if (mo.outer_type == 3 || mo.outer_type == 4) {
+    RC(op_cg_normal(e, alg, s, global, mo.outer_type == 4, mo.max_it, mo.rtol, mo.abstol, alpha, &norm, &lits));
+  } else {
+    std::vector<double> uaug((size_t)(s + 1) * (s + 1));
+    RC(op_local_qr(e, alg, s, uaug.data()));
+    if (global && G > 1) {
+      // TSQR: gather every block's factor (zero-padded allreduce = allgather), identical small solve everywhere
+      const int nn = (s + 1) * (s + 1);
+      std::vector<double> all((size_t)G * nn, 0.0);
+      memcpy(all.data() + (size_t)e->prob.block * nn, uaug.data(), sizeof(double) * nn);
+      CK(cudaMemcpyAsync(e->dfac, all.data(), sizeof(double) * (size_t)G * nn, cudaMemcpyHostToDevice, e->st));
+      RC(e->comm->allreduce_sum(e->dfac, G * nn, e->st));
+      CK(cudaMemcpyAsync(all.data(), e->dfac, sizeof(double) * (size_t)G * nn, cudaMemcpyDeviceToHost, e->st));
+      CK(cudaStreamSynchronize(e->st));
+      RC(tsqr_combine(s, G, all.data(), alpha, &norm));
+    } else {
+      RC(tsqr_combine(s, 1, uaug.data(), alpha, &norm));
+    }
+  }
+  RC(op_apply_alpha(e, alg, s, alpha));
+  if (norm_out) *norm_out = norm;
+  if (lits_out) *lits_out = lits;
+  return 0;
+}
+
+static inline void record_hist(const msp_solve_opts *o, msp_result *res, double v) {
+  if (!o->record_history) return;
+  if (res->hist_len < 4096) res->hist[res->hist_len++] = v;
+  else res->hist_dropped++;
+}
+struct EventPair { // destroyed on every return path
+  cudaEvent_t a = nullptr, b = nullptr;
+  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+// wall-clock cap: every block must leave the loop at the same outer iteration, so the local verdicts are summed
+static int agree_time_up(msp_engine *e, const msp_solve_opts *o, std::chrono::steady_clock::time_point t_start, bool *stop) {
+  *stop = false;
+  if (!(o->max_seconds > 0.0)) return 0;
+  const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+  e->hsc[7] = (el >= o->max_seconds) ? 1.0 : 0.0;
+  if (e->comm->nranks > 1) {
+    CK(cudaMemcpyAsync(e->dsc + 7, e->hsc + 7, sizeof(double), cudaMemcpyHostToDevice, e->st));
+    RC(allreduce_host(e, 7, 1));
+  }
+  *stop = e->hsc[7] > 0.0;
+  return 0;
+}
+
 static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result *res) {
   const int G = e->prob.nblocks, s = o->s;
   const int alg = o->alg;
@@ -37,21 +99,24 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
   const double thr_global = std::max(atol, o->rtol * res->norm0);
   const double thr_local = std::max(atol, (o->rtol / std::sqrt((double)G)) * 1.0 * res->norm0);
   RC(e->comm->barrier(e->st)); // PetscBarrier before MPI_Wtime
-  cudaEvent_t ev0, ev1;
-  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
-  CK(cudaEventRecord(ev0, e->st));
+  EventPair ev;
+  CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
+  CK(cudaEventRecord(ev.a, e->st));
   const int64_t launches0 = e->launches;
   e->prof = o->profile != 0;
-  bool done = false;
+  struct ProfOff { msp_engine *e; ~ProfOff() { e->prof = false; } } prof_off{e};
+  bool done = false, time_up = false;
+  const auto t_start = std::chrono::steady_clock::now();
   int sticky = 0;
   const bool lsqr = o->outer_type == 1;
   const int lsqr_max_it = o->outer_max_it > 0 ? o->outer_max_it : 100;
   const double lsqr_rtol = o->outer_rtol > 0 ? o->outer_rtol : 1e-15, lsqr_abstol = o->outer_abstol > 0 ? o->outer_abstol : 1e-100;
   typedef std::chrono::steady_clock clk;
   auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
-  std::vector<double> uaug((size_t)(s + 1) * (s + 1)), alpha(std::max(s, 1));
+  std::vector<double> alpha(std::max(s, 1));
+  const MinimizeOpts mo{o->outer_type, lsqr_max_it, lsqr_rtol, lsqr_abstol};
   if (alg == MSP_ALG_SM) RC(op_update_rhs(e)); // …multisplitting.c:164
-  while (!done && res->outer_its < max_outer) {
+  while (!done && !time_up && res->outer_its < max_outer) {
     if (alg == MSP_ALG_SM) {
       int its = 0, reason = 0;
       auto t0 = clk::now();
@@ -65,10 +130,11 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
       RC(allreduce_host(e, 0, 1));
       const double norm = std::sqrt(e->hsc[0]);
       res->last_norm = norm;
-      if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = norm;
+      record_hist(o, res, norm);
       if (norm <= thr_global) done = true;
       res->outer_its++;
       res->stage_outer_s += secs(t1, clk::now());
+      if (!done) RC(agree_time_up(e, o, t_start, &time_up));
       continue;
     }
     auto t_outer0 = clk::now();
@@ -83,100 +149,49 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
       RC(exchange_sync(e));
       RC(op_push_iterate(e, t));
     }
-    if (lsqr || o->outer_type == 2) {
-      // the reference's minimisers, literally: LSQR on R = A S with the raw basis (utils.c:1061-1103), or the normal
-      // equations on the Gram matrix (utils.c:972-996; basis of successive corrections to keep it solvable)
-      int lits = 0;
-      double norm = 0.0;
-      RC(op_spmm(e, alg, s, !lsqr));
-      if (alg == MSP_ALG_SMSM_LOCAL) RC(op_update_rhs(e));
-      double ln = 0.0;
-      if (alg == MSP_ALG_SMSM_SEMI_LOCAL) { RC(op_resid_sumsq(e, false, 1)); RC(read_scalars(e, 1, 1)); ln = std::sqrt(e->hsc[1]); }
-      if (lsqr) RC(op_lsqr(e, alg, s, alg == MSP_ALG_SMSM_GLOBAL, lsqr_max_it, lsqr_rtol, lsqr_abstol, alpha.data(), &norm, &lits));
-      else RC(op_normal_equations(e, alg, s, alg == MSP_ALG_SMSM_GLOBAL, alpha.data(), &norm));
-      res->outer_solver_its += lits;
-      RC(op_apply_alpha(e, alg, s, alpha.data()));
-      if (alg == MSP_ALG_SMSM_GLOBAL) {
-        res->last_norm = norm; // KSPGetResidualNorm(outer_ksp) = phibar (…-global.c:343)
-        if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = norm;
-        if (norm <= thr_global) done = true;
-      } else {
-        if (alg == MSP_ALG_SMSM_LOCAL) { RC(op_resid_sumsq(e, false, 1)); RC(read_scalars(e, 1, 1)); ln = std::sqrt(e->hsc[1]); }
-        if (ln <= thr_local) sticky = 1;
-        e->hsc[2] = sticky; e->hsc[3] = ln * ln;
-        CK(cudaMemcpyAsync(e->dsc + 2, e->hsc + 2, 16, cudaMemcpyHostToDevice, e->st));
-        RC(allreduce_host(e, 2, 2));
-        res->last_norm = ln;
-        if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = ln;
-        if ((int)std::lround(e->hsc[2]) == G) done = true;
-      }
-    } else if (alg == MSP_ALG_SMSM_GLOBAL) {
-      RC(op_spmm(e, alg, s));
-      RC(op_local_qr(e, alg, s, uaug.data()));
-      // TSQR: gather every block's factor (zero-padded allreduce = allgather), identical small solve everywhere
-      const int nn = (s + 1) * (s + 1);
-      std::vector<double> all((size_t)G * nn, 0.0);
-      if (G > 1) {
-        memcpy(all.data() + (size_t)e->prob.block * nn, uaug.data(), sizeof(double) * nn);
-        CK(cudaMemcpyAsync(e->dfac, all.data(), sizeof(double) * (size_t)G * nn, cudaMemcpyHostToDevice, e->st));
-        RC(e->comm->allreduce_sum(e->dfac, G * nn, e->st));
-        CK(cudaMemcpyAsync(all.data(), e->dfac, sizeof(double) * (size_t)G * nn, cudaMemcpyDeviceToHost, e->st));
-        CK(cudaStreamSynchronize(e->st));
-      } else {
-        all = uaug;
-      }
-      double norm = 0.0;
-      RC(tsqr_combine(s, G, all.data(), alpha.data(), &norm));
-      RC(op_apply_alpha(e, alg, s, alpha.data()));
-      res->last_norm = norm;
-      if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = norm;
+    // R = A S (MatMatMult …-global.c:326); the LSQR path keeps the reference's raw basis [x^1 .. x^s], the exact solvers
+    // use the basis of successive corrections
+    RC(op_spmm(e, alg, s, !lsqr));
+    int lits = 0;
+    double norm = 0.0, ln = 0.0;
+    if (alg == MSP_ALG_SMSM_GLOBAL) {
+      RC(op_minimize(e, alg, s, mo, alpha.data(), &norm, &lits));
+      res->last_norm = norm; // KSPGetResidualNorm(outer_ksp) = phibar (…-global.c:343) = ||b - R alpha||
+      record_hist(o, res, norm);
       if (norm <= thr_global) done = true;
-    } else if (alg == MSP_ALG_SMSM_SEMI_LOCAL) {
-      RC(op_spmm(e, alg, s));
-      RC(op_local_qr(e, alg, s, uaug.data()));
-      RC(tsqr_combine(s, 1, uaug.data(), alpha.data(), nullptr));
-      RC(op_resid_sumsq(e, false, 1)); // pre-minimisation x_K against the stale rhs_K (…-semi-local.c:326)
-      RC(read_scalars(e, 1, 1));
-      const double ln = std::sqrt(e->hsc[1]);
-      if (ln <= thr_local) sticky = 1;
-      RC(op_apply_alpha(e, alg, s, alpha.data()));
-      e->hsc[2] = sticky; e->hsc[3] = ln * ln;
-      CK(cudaMemcpyAsync(e->dsc + 2, e->hsc + 2, 16, cudaMemcpyHostToDevice, e->st));
-      RC(allreduce_host(e, 2, 2));
-      res->last_norm = ln;
-      if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = ln;
-      if ((int)std::lround(e->hsc[2]) == G) done = true; // comm_sync_convergence_detection comm.c:235-250
-    } else if (alg == MSP_ALG_SMSM_LOCAL) {
-      RC(op_spmm(e, alg, s));
-      RC(op_update_rhs(e));
-      RC(op_local_qr(e, alg, s, uaug.data()));
-      RC(tsqr_combine(s, 1, uaug.data(), alpha.data(), nullptr));
-      RC(op_apply_alpha(e, alg, s, alpha.data()));
-      RC(op_resid_sumsq(e, false, 1));
-      RC(read_scalars(e, 1, 1));
-      const double ln = std::sqrt(e->hsc[1]);
-      if (ln <= thr_local) sticky = 1;
-      e->hsc[2] = sticky; e->hsc[3] = ln * ln;
-      CK(cudaMemcpyAsync(e->dsc + 2, e->hsc + 2, 16, cudaMemcpyHostToDevice, e->st));
-      RC(allreduce_host(e, 2, 2));
-      res->last_norm = ln;
-      if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = ln;
-      if ((int)std::lround(e->hsc[2]) == G) done = true;
     } else {
-      MSP_FAIL("algorithm not handled by the synchronous driver");
+      if (alg == MSP_ALG_SMSM_SEMI_LOCAL) {
+        // pre-minimisation x_K against the stale rhs_K (…-semi-local.c:326)
+        RC(op_resid_sumsq(e, false, 1)); RC(read_scalars(e, 1, 1)); ln = std::sqrt(e->hsc[1]);
+      } else if (alg == MSP_ALG_SMSM_LOCAL) {
+        RC(op_update_rhs(e)); // …-local.c:258
+      } else {
+        MSP_FAIL("algorithm not handled by the synchronous driver");
+      }
+      RC(op_minimize(e, alg, s, mo, alpha.data(), nullptr, &lits));
+      if (alg == MSP_ALG_SMSM_LOCAL) { RC(op_resid_sumsq(e, false, 1)); RC(read_scalars(e, 1, 1)); ln = std::sqrt(e->hsc[1]); }
+      if (ln <= thr_local) sticky = 1;
+      e->hsc[2] = sticky; e->hsc[3] = ln * ln;
+      CK(cudaMemcpyAsync(e->dsc + 2, e->hsc + 2, 16, cudaMemcpyHostToDevice, e->st));
+      RC(allreduce_host(e, 2, 2));
+      res->last_norm = ln;
+      record_hist(o, res, ln);
+      if ((int)std::lround(e->hsc[2]) == G) done = true; // comm_sync_convergence_detection comm.c:235-250
     }
+    res->outer_solver_its += lits;
     res->outer_its++;
     res->stage_inner_s += inner_this;
     res->stage_outer_s += secs(t_outer0, clk::now()) - inner_this;
+    if (!done) RC(agree_time_up(e, o, t_start, &time_up));
   }
+  res->stop_reason = done ? MSP_STOP_CONVERGED : time_up ? MSP_STOP_MAX_SECONDS : MSP_STOP_MAX_OUTER;
   RC(e->comm->barrier(e->st));
-  CK(cudaEventRecord(ev1, e->st));
-  CK(cudaEventSynchronize(ev1));
+  CK(cudaEventRecord(ev.b, e->st));
+  CK(cudaEventSynchronize(ev.b));
   float ms = 0.f;
-  CK(cudaEventElapsedTime(&ms, ev0, ev1));
+  CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
   res->elapsed_s = ms * 1e-3;
   res->kernel_launches = e->launches - launches0;
-  CK(cudaEventDestroy(ev0)); CK(cudaEventDestroy(ev1));
   e->prof_collect(res);
   e->prof = false;
   // closing exchange + true residual + error (comm_sync_send_and_receive_final comm.c:199, utils.c:575, :1045)
@@ -202,18 +217,17 @@ static int engine_gmres(msp_engine *e, const msp_ksp_opts *o, msp_result *res) {
   res->norm0 = std::sqrt(e->hsc[0]);
   msp_ksp_opts in = *o;
   in.guess_nonzero = 0;
-  cudaEvent_t ev0, ev1;
-  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
-  CK(cudaEventRecord(ev0, e->st));
+  EventPair ev;
+  CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
+  CK(cudaEventRecord(ev.a, e->st));
   const int64_t l0 = e->launches;
   RC(op_inner_solve(e, &in, false, &res->gmres_its, &res->gmres_reason, &res->gmres_rnorm));
-  CK(cudaEventRecord(ev1, e->st));
-  CK(cudaEventSynchronize(ev1));
+  CK(cudaEventRecord(ev.b, e->st));
+  CK(cudaEventSynchronize(ev.b));
   float ms = 0.f;
-  CK(cudaEventElapsedTime(&ms, ev0, ev1));
+  CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
   res->elapsed_s = ms * 1e-3;
   res->kernel_launches = e->launches - l0;
-  CK(cudaEventDestroy(ev0)); CK(cudaEventDestroy(ev1));
   res->outer_its = res->gmres_its;
   res->last_norm = res->gmres_rnorm;
   RC(op_resid_sumsq(e, true, 0));
@@ -232,6 +246,19 @@ struct msp_group {
   std::vector<msp_engine *> eng;
   LocalShared *sh = nullptr;
 };
+
+// the error a group call reports: the first block failure that is not just the echo of another block's abort
+static int group_first_error(const std::vector<int> &rcs, const std::vector<std::string> &errs) {
+  int first = -1;
+  for (size_t k = 0; k < rcs.size(); k++)
+    if (rcs[k]) {
+      if (first < 0) first = (int)k;
+      if (errs[k].find("group aborted") == std::string::npos) { first = (int)k; break; }
+    }
+  if (first < 0) return 0;
+  g_err = errs[first];
+  return rcs[first];
+}
 
 static int group_wire(msp_group *g) {
   for (int k = 0; k < g->G; k++) {
@@ -420,7 +447,7 @@ static int async_step(msp_engine *e, const msp_solve_opts *o, msp_result *res, A
   run->last_norm = std::sqrt(e->hsc[1]);
   run->iters++;
   res->last_norm = run->last_norm;
-  if (o->record_history && res->hist_len < 4096) res->hist[res->hist_len++] = run->last_norm;
+  record_hist(o, res, run->last_norm);
   return 0;
 }
 
@@ -446,7 +473,12 @@ static int engine_solve_async(msp_engine *e, const msp_solve_opts *o, msp_result
   const int max_outer = o->max_outer > 0 ? o->max_outer : 1000000;
   const int64_t l0 = e->launches;
   auto t0 = std::chrono::steady_clock::now();
-  while (run.state != 3 && run.iters < max_outer) RC(async_step(e, o, res, &run));
+  bool time_up = false;
+  while (run.state != 3 && run.iters < max_outer && !time_up) {
+    RC(async_step(e, o, res, &run));
+    if (o->max_seconds > 0.0) time_up = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= o->max_seconds;
+  }
+  res->stop_reason = run.state == 3 ? MSP_STOP_CONVERGED : time_up ? MSP_STOP_MAX_SECONDS : MSP_STOP_MAX_OUTER;
   CK(cudaStreamSynchronize(e->st));
   res->elapsed_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   res->kernel_launches = e->launches - l0;
@@ -460,17 +492,17 @@ static int engine_solve_async_group(msp_group *g, const msp_solve_opts *o, msp_r
   for (int k = 0; k < G; k++) scheduled |= (o->period[k] > 0);
   std::vector<int> rcs(G, 0);
   std::vector<std::string> errs(G);
+  g->sh->reset();
   if (!scheduled) {
     std::vector<std::thread> th;
     for (int k = 0; k < G; k++)
       th.emplace_back([&, k] {
         cudaSetDevice(g->eng[k]->device);
         rcs[k] = engine_solve_async(g->eng[k], o, &res[k]);
-        if (rcs[k]) errs[k] = g_err;
+        if (rcs[k]) { errs[k] = g_err; g->sh->abort(); }
       });
     for (auto &t : th) t.join();
-    for (int k = 0; k < G; k++) if (rcs[k]) { g_err = errs[k]; return rcs[k]; }
-    return 0;
+    return group_first_error(rcs, errs);
   }
   // deterministic schedule (tests): block K runs one step at tick t iff t % period[K] == 0, blocks in index order;
   // collective phases (norm0, closing exchange) still need one thread per block
@@ -478,10 +510,9 @@ static int engine_solve_async_group(msp_group *g, const msp_solve_opts *o, msp_r
   auto par_all = [&](auto fn) {
     std::vector<std::thread> th;
     for (int k = 0; k < G; k++)
-      th.emplace_back([&, k] { cudaSetDevice(g->eng[k]->device); rcs[k] = fn(k); if (rcs[k]) errs[k] = g_err; });
+      th.emplace_back([&, k] { cudaSetDevice(g->eng[k]->device); rcs[k] = fn(k); if (rcs[k]) { errs[k] = g_err; g->sh->abort(); } });
     for (auto &t : th) t.join();
-    for (int k = 0; k < G; k++) if (rcs[k]) { g_err = errs[k]; return rcs[k]; }
-    return 0;
+    return group_first_error(rcs, errs);
   };
   RC(par_all([&](int k) { int rc = async_begin(g->eng[k], o, &res[k], &runs[k]); if (!rc) rc = g->eng[k]->comm->barrier(g->eng[k]->st); return rc; }));
   const long long max_ticks = (long long)(o->max_outer > 0 ? o->max_outer : 1000000) * 64;

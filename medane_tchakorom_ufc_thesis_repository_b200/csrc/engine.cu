@@ -352,6 +352,25 @@ static int engine_free(msp_engine *e) {
   return 0;
 }
 
+// b_K = A_K,: * 1 (computeTheRightHandSideWithInitialGuess utils.c:623-626): the strip product with halos of ones; the
+// private halos are zero afterwards (x0 = 0 on every block) and rhs_K = b_K.  The reference's Sendrecv of b_J (utils.c:637)
+// has no counterpart: no block ever needs another block's right-hand side here.
+static int op_compute_rhs_ones(msp_engine *e) {
+  const size_t vb = sizeof(double) * (size_t)e->ld;
+  k_fill<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, 1.0, e->Wb[0]);
+  k_fill<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->H, 1.0, e->halo[0]);
+  k_fill<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->H, 1.0, e->halo[1]);
+  SpmvArgs a = spmv_args(e, e->Wb[0], e->b);
+  a.lo = e->has_nb[0] ? e->halo[0] : nullptr; a.hi = e->has_nb[1] ? e->halo[1] : nullptr;
+  launch_spmv_w<1, false, false, false>(e, a, 0, nullptr);
+  CK(cudaMemsetAsync(e->halo[0], 0, sizeof(double) * e->H, e->st));
+  CK(cudaMemsetAsync(e->halo[1], 0, sizeof(double) * e->H, e->st));
+  CK(cudaMemsetAsync(e->Wb[0], 0, vb, e->st));
+  CK(cudaMemcpyAsync(e->rhs, e->b, vb, cudaMemcpyDeviceToDevice, e->st));
+  CK(cudaGetLastError());
+  return 0;
+}
+
 static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   if (!p || !out) MSP_FAIL("null argument");
   if (p->dim != 2 && p->dim != 3) MSP_FAIL("dim must be 2 or 3");
@@ -497,8 +516,8 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   if (ok) cudaMemsetAsync(e->dec, 0, sizeof(ProbeDecision) * 2, e->st);
   e->fcache.assign((size_t)p->nblocks * e->win.fslot, 0.0);
   e->fcache_seq.assign(p->nblocks, 0);
-  if (ok && cudaMalloc(&e->ws.counter, sizeof(unsigned) * 64) != cudaSuccess) ok = false;
-  if (ok) cudaMemsetAsync(e->ws.counter, 0, sizeof(unsigned) * 64, e->st);
+  if (ok && cudaMalloc(&e->ws.counter, sizeof(unsigned) * MSPK_NCOUNTER) != cudaSuccess) ok = false;
+  if (ok) cudaMemsetAsync(e->ws.counter, 0, sizeof(unsigned) * MSPK_NCOUNTER, e->st);
   if (ok && cudaMalloc(&e->ctl, sizeof(GmresCtl)) != cudaSuccess) ok = false;
   if (ok) cudaMemsetAsync(e->ctl, 0, sizeof(GmresCtl), e->st);
   if (ok && cudaMalloc(&e->cd, sizeof(CdState)) != cudaSuccess) ok = false;
@@ -507,19 +526,7 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   if (!ok) { g_err = "out of device memory (vectors)"; return fail(1); }
   e->comm = new SelfComm(); e->own_comm = true;
   e->use_graphs = getenv("MSPLIT_NO_GRAPHS") == nullptr;
-  // ---- b_K = A_K,: * 1 (computeTheRightHandSideWithInitialGuess utils.c:626): halos of ones ----
-  {
-    k_fill<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, 1.0, e->Wb[0]);
-    k_fill<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->H, 1.0, e->halo[0]);
-    k_fill<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->H, 1.0, e->halo[1]);
-    SpmvArgs a = spmv_args(e, e->Wb[0], e->b);
-    a.lo = e->has_nb[0] ? e->halo[0] : nullptr; a.hi = e->has_nb[1] ? e->halo[1] : nullptr;
-    launch_spmv_w<1, false, false, false>(e, a, 0, nullptr);
-    cudaMemsetAsync(e->halo[0], 0, sizeof(double) * e->H, e->st);
-    cudaMemsetAsync(e->halo[1], 0, sizeof(double) * e->H, e->st);
-    cudaMemsetAsync(e->Wb[0], 0, vb, e->st);
-    cudaMemcpyAsync(e->rhs, e->b, vb, cudaMemcpyDeviceToDevice, e->st);
-  }
+  if (op_compute_rhs_ones(e)) return fail(1);
   if (cudaStreamSynchronize(e->st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { g_err = "setup kernels failed"; return fail(1); }
   e->launches = 0;
   *out = e;

@@ -51,9 +51,11 @@ struct GmresCtl {
   double hh[(MSPK_MAXK + 2) * (MSPK_MAXK + 1)]; // column-major, ld = MSPK_MAXK + 2
 };
 
+#define MSPK_NCOUNTER 128      // reduction tickets: 0..7 norm slots, 8..8+63 MDot groups (<= 64 groups), 120 Gram kernel
+#define MSPK_GRAM_COUNTER 120
 struct ReduceWs {       // workspace of the last-block-done reductions
-  double *partial;      // [MSPK_MAX_PART * 16]
-  unsigned int *counter; // [64]
+  double *partial;      // [MSPK_MAX_PART * 192]
+  unsigned int *counter; // [MSPK_NCOUNTER]
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -461,7 +463,8 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_spmv_dia(SpmvArgs a, ReduceWs 
       const double2 v = ld_stream2(a.dval + k * a.ld + r);
       const int c = (int)r + a.dia.off[k];
       const double x0 = gather_x<MODE>(a, c, inv, SCALE);
-      const double x1 = gather_x<MODE>(a, c + 1, inv, SCALE);
+      // the second row of the last pair does not exist when nb is odd: no gather (its column may lie past the halo)
+      const double x1 = (r + 1 < a.nb) ? gather_x<MODE>(a, c + 1, inv, SCALE) : 0.0;
       s0 = fma(v.x, x0, s0);
       s1 = fma(v.y, x1, s1);
     }

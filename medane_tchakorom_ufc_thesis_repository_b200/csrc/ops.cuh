@@ -43,7 +43,9 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
     e->launches++;
     bnorm_sq = e->dsc + 8;
   }
-  k_ctl_begin<<<1, 32, 0, e->st>>>(e->ctl, o->restart, o->max_it, o->min_it, o->initial_rtol, guess_zero ? 1 : 0, o->cgs_refine, o->rtol,
+  // PETSc ignores -ksp_gmres_cgs_refinement_type under modified Gram-Schmidt: the MGS step has no second pass
+  const int cgs_refine = o->mgs ? 0 : o->cgs_refine;
+  k_ctl_begin<<<1, 32, 0, e->st>>>(e->ctl, o->restart, o->max_it, o->min_it, o->initial_rtol, guess_zero ? 1 : 0, cgs_refine, o->rtol,
                                    o->abstol, o->divtol, bnorm_sq);
   e->launches++;
   int itcount = 0;
@@ -93,7 +95,7 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
         // classical Gram-Schmidt: lhh = -V^T w (K3); w += V lhh, ||w|| (K4+K5), Hessenberg + test (K6)
         launch_mdot(e, it + 1, e->V, e->ld, w, lhh, -1.0, it, 0, invs);
         launch_maxpy<1>(e, it + 1, e->V, e->ld, lhh, w, nullptr, it, 0, 0, 0, invs);
-        if (o->cgs_refine) {
+        if (cgs_refine) {
           launch_mdot(e, it + 1, e->V, e->ld, w, lhh, -1.0, it, 1, invs);
           launch_maxpy<1>(e, it + 1, e->V, e->ld, lhh, w, nullptr, it, 1, 1, 0, invs);
         }
@@ -108,7 +110,7 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
       return 0;
     };
     if (e->use_graphs && !e->prof) {
-      const msp_engine::CycleKey key(nsteps, o->cgs_refine + 4 * (o->mgs ? 1 : 0), from_rhs ? 1 : 0, (const void *)e->V, (const void *)peer_lo, (const void *)peer_hi);
+      const msp_engine::CycleKey key(nsteps, cgs_refine + 4 * (o->mgs ? 1 : 0), from_rhs ? 1 : 0, (const void *)e->V, (const void *)peer_lo, (const void *)peer_hi);
       auto itg = e->cycle_graphs.find(key);
       if (itg == e->cycle_graphs.end()) {
         const int64_t l0 = e->launches;
@@ -136,6 +138,7 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
     itcount += hc.it;
     if (hc.reason) break;
     if (itcount >= o->max_it) { hc.reason = MSP_DIVERGED_ITS; break; }
+    if (hc.it == 0) { hc.reason = MSP_DIVERGED_BREAKDOWN; break; } // a cycle that made no step can never end the loop
   }
   if (its_out) *its_out = hc.its;
   if (reason_out) *reason_out = hc.reason;
@@ -244,7 +247,7 @@ static bool chol_upper(int nc, const double *G, double *U) {
 template <int NC>
 static void launch_gram_nc(msp_engine *e, const double *C, double *out_dev) {
   auto k = k_gram<NC>;
-  k<<<grid_for((long long)e->nb / 2, std::min(resident_blocks_per_sm(k), 4)), MSPK_THREADS, 0, e->st>>>(e->nb, e->ld, C, e->gram_partial, e->ws.counter + 40, out_dev);
+  k<<<grid_for((long long)e->nb / 2, std::min(resident_blocks_per_sm(k), 4)), MSPK_THREADS, 0, e->st>>>(e->nb, e->ld, C, e->gram_partial, e->ws.counter + MSPK_GRAM_COUNTER, out_dev);
   e->launches++;
 }
 template <int NC>
@@ -485,6 +488,115 @@ static int op_normal_equations(msp_engine *e, int kind, int s, bool global, doub
     }
     *rnorm_out = std::sqrt(e->hsc[6]);
   }
+  return 0;
+}
+
+// The reference's two remaining outer solvers:
+//  * `outer_solver` utils.c:972-996 with -outer_ksp_type cg (config/default_run_variables: cg, max_it 100000, rtol 1e-20):
+//    MatTransposeMatMult(R,R) and MatMultTranspose(R,b) explicitly, then KSPCG on the s x s system.  Here: ONE Gram pass
+//    over [R_K | rhs] (K9) (+ one allreduce of the (s+1)^2 entries when global), PETSc's CG recurrence (cg.c, PC none,
+//    zero guess, initial-residual-norm test on the natural residual) on the host — the system is s x s.
+//  * `outer_solver_cgne` utils.c:1020-1043 (KSPCGNE on R itself): CG on the normal equations WITHOUT forming R'R —
+//    every iteration is w = R p (K10), z = R' r (K3) and r -= a w (K4+K5) on the device, s-vectors on the host.
+// Both return ||rhs - R alpha|| (second pass / the maintained residual), the quantity the global driver stops on.
+static int op_cg_normal(msp_engine *e, int kind, int s, bool global, bool cgne, int max_it, double rtol, double abstol, double *alpha,
+                        double *rnorm_out, int *its_out) {
+  const double *rhs_src = kind_is_local(kind) ? e->rhs : e->b;
+  auto sum_blocks = [&](int first, int n) -> int { return global ? allreduce_host(e, first, n) : read_scalars(e, first, n); };
+  for (int j = 0; j < s; j++) alpha[j] = 0.0;
+  int its = 0;
+  if (!cgne) {
+    const int nc = s + 1;
+    if (nc > 9) MSP_FAIL("the CG-on-normal-equations minimiser supports s <= 8");
+    double *bcol = e->R + (long long)s * e->ld;
+    k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, rhs_src, bcol);
+    e->launches++;
+    launch_gram(e, nc, e->R, e->dfac);
+    if (global) RC(e->comm->allreduce_sum(e->dfac, nc * nc, e->st));
+    std::vector<double> G((size_t)nc * nc);
+    CK(cudaMemcpyAsync(G.data(), e->dfac, sizeof(double) * nc * nc, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    auto A = [&](int i, int j) { return i <= j ? G[(size_t)j * nc + i] : G[(size_t)i * nc + j]; }; // upper triangle stored
+    std::vector<double> r(s), p(s, 0.0), w(s);
+    for (int i = 0; i < s; i++) r[i] = A(i, s); // R'b; x = 0
+    double beta = 0.0, betaold = 1.0;
+    for (int i = 0; i < s; i++) beta += r[i] * r[i];
+    double dp = std::sqrt(beta);
+    const double ttol = std::max(rtol * dp, abstol);
+    if (beta > 0.0 && dp > ttol) {
+      for (int i = 0; i < max_it; i++) {
+        if (i == 0) p = r;
+        else { const double b = beta / betaold; for (int k = 0; k < s; k++) p[k] = r[k] + b * p[k]; }
+        double dpi = 0.0;
+        for (int k = 0; k < s; k++) { double t = 0.0; for (int l = 0; l < s; l++) t += A(k, l) * p[l]; w[k] = t; dpi += p[k] * t; }
+        if (!(dpi > 0.0)) break; // KSP_DIVERGED_INDEFINITE_MAT (or NaN): keep the iterate
+        const double a = beta / dpi;
+        for (int k = 0; k < s; k++) { alpha[k] += a * p[k]; r[k] -= a * w[k]; }
+        betaold = beta;
+        beta = 0.0;
+        for (int k = 0; k < s; k++) beta += r[k] * r[k];
+        dp = std::sqrt(beta);
+        its++;
+        if (beta == 0.0 || dp <= ttol || std::isnan(dp)) break;
+      }
+    }
+    if (rnorm_out) {
+      for (int j = 0; j < s; j++) e->hsc[216 + j] = -alpha[j];
+      CK(cudaMemcpyAsync(e->dsc + 216, e->hsc + 216, sizeof(double) * s, cudaMemcpyHostToDevice, e->st));
+      launch_maxpy<0>(e, s, e->R, e->ld, e->dsc + 216, bcol, e->dsc + 6, -1, 0, 0, 3);
+      RC(read_scalars(e, 6, 1));
+      e->hsc[6] = e->hsc[6] * e->hsc[6];
+      if (global) { CK(cudaMemcpyAsync(e->dsc + 6, e->hsc + 6, sizeof(double), cudaMemcpyHostToDevice, e->st)); RC(allreduce_host(e, 6, 1)); }
+      *rnorm_out = std::sqrt(e->hsc[6]);
+    }
+    if (its_out) *its_out = its;
+    return 0;
+  }
+  // ---- CGNE: r = rhs (x = 0), z = R' r, p = z; { w = R p; a = |z|^2 / |w|^2; x += a p; r -= a w; z = R' r; p = z + (|z|^2/|z_old|^2) p }
+  double *Rv = e->Wb[0], *Wv = e->Wb[1];
+  std::vector<double> z(s), p(s, 0.0);
+  k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, rhs_src, Rv);
+  k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, Rv, 0.0, e->ws, 2, e->dsc + 4);
+  e->launches += 2;
+  RC(sum_blocks(4, 1));
+  double rn = std::sqrt(e->hsc[4]);
+  launch_mdot(e, s, e->R, e->ld, Rv, e->dsc + 64, 1.0, -1, 0);
+  RC(sum_blocks(64, s));
+  double beta = 0.0, betaold = 1.0;
+  for (int j = 0; j < s; j++) { z[j] = e->hsc[64 + j]; beta += z[j] * z[j]; }
+  const double ttol = std::max(rtol * std::sqrt(beta), abstol);
+  if (beta > 0.0 && std::sqrt(beta) > ttol) {
+    for (int i = 0; i < max_it; i++) {
+      if (i == 0) p = z;
+      else { const double b = beta / betaold; for (int k = 0; k < s; k++) p[k] = z[k] + b * p[k]; }
+      memcpy(e->hsc + 216, p.data(), sizeof(double) * s);
+      CK(cudaMemcpyAsync(e->dsc + 216, e->hsc + 216, sizeof(double) * s, cudaMemcpyHostToDevice, e->st));
+      k_lincomb<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, s, e->ld, e->R, e->dsc + 216, Wv); // w = R p
+      k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, Wv, 0.0, e->ws, 2, e->dsc + 5);
+      e->launches += 2;
+      RC(sum_blocks(5, 1));
+      const double dpi = e->hsc[5];
+      if (!(dpi > 0.0)) break;
+      const double a = beta / dpi;
+      for (int k = 0; k < s; k++) alpha[k] += a * p[k];
+      e->hsc[5] = -a;
+      CK(cudaMemcpyAsync(e->dsc + 5, e->hsc + 5, sizeof(double), cudaMemcpyHostToDevice, e->st));
+      launch_maxpy<0>(e, 1, Wv, e->ld, e->dsc + 5, Rv, e->dsc + 6, -1, 0, 0, 3); // r -= a w, ||r||
+      RC(read_scalars(e, 6, 1));
+      e->hsc[6] = e->hsc[6] * e->hsc[6];
+      if (global) { CK(cudaMemcpyAsync(e->dsc + 6, e->hsc + 6, sizeof(double), cudaMemcpyHostToDevice, e->st)); RC(allreduce_host(e, 6, 1)); }
+      rn = std::sqrt(e->hsc[6]);
+      launch_mdot(e, s, e->R, e->ld, Rv, e->dsc + 64, 1.0, -1, 0); // z = R' r
+      RC(sum_blocks(64, s));
+      betaold = beta;
+      beta = 0.0;
+      for (int j = 0; j < s; j++) { z[j] = e->hsc[64 + j]; beta += z[j] * z[j]; }
+      its++;
+      if (beta == 0.0 || std::sqrt(beta) <= ttol || std::isnan(beta)) break;
+    }
+  }
+  if (rnorm_out) *rnorm_out = rn;
+  if (its_out) *its_out = its;
   return 0;
 }
 

@@ -249,12 +249,29 @@ API void orc_ksp_defaults(orc_ksp_opts *o) {
 /* restarted GMRES  (PETSc gmres.c KSPSolve_GMRES / KSPGMRESCycle /         */
 /* KSPGMRESUpdateHessenberg / KSPGMRESBuildSoln, borthog2.c) */
 /* ======================================================================= */
+static struct { int n, m; double **V; } g_gmres_ws = {0, 0, NULL};
+API void orc_gmres_release_workspace(void) {
+  if (g_gmres_ws.V) {
+    for (int i = 0; i < g_gmres_ws.m + 2; i++) free(g_gmres_ws.V[i]);
+    free(g_gmres_ws.V);
+  }
+  g_gmres_ws.V = NULL; g_gmres_ws.n = g_gmres_ws.m = 0;
+}
+static double **gmres_workspace(int n, int m) {
+  if (g_gmres_ws.V && g_gmres_ws.n == n && g_gmres_ws.m == m) return g_gmres_ws.V;
+  orc_gmres_release_workspace();
+  g_gmres_ws.V = (double **)malloc(sizeof(double *) * (m + 2));
+  for (int i = 0; i < m + 2; i++) g_gmres_ws.V[i] = (double *)malloc(sizeof(double) * (size_t)n);
+  g_gmres_ws.n = n; g_gmres_ws.m = m;
+  return g_gmres_ws.V;
+}
 API int orc_gmres(int n, const int32_t *rowptr, const int32_t *colidx, const double *val, const double *b, double *x,
                   const orc_ksp_opts *o, int *its_out, int *reason_out, double *rnorm_out, double *hist, int hist_cap) {
   const int m = o->restart;
   const double haptol = 1e-30, breakdowntol = 0.1;
-  double **V = (double **)malloc(sizeof(double *) * (m + 2));
-  for (int i = 0; i < m + 2; i++) V[i] = (double *)malloc(sizeof(double) * (size_t)n);
+  /* Krylov workspace kept between calls (PETSc allocates VEC_VV once per KSP, not once per KSPSolve): at 67 M rows a
+   * fresh malloc per inner solve would page-fault ~11 GB every time and inflate the CPU baseline. */
+  double **V = gmres_workspace(n, m);
   double *temp = V[m + 1];
   /* HH is (m+1) x m, column-major with leading dimension m+1 */
   double *HH = (double *)calloc((size_t)(m + 2) * (m + 1), sizeof(double));
@@ -379,8 +396,7 @@ API int orc_gmres(int n, const int32_t *rowptr, const int32_t *colidx, const dou
   if (its_out) *its_out = its;
   if (reason_out) *reason_out = reason;
   if (rnorm_out) *rnorm_out = ksp_rnorm;
-  for (int i = 0; i < m + 2; i++) free(V[i]);
-  free(V); free(HH); free(cc); free(ss); free(grs); free(lhh);
+  free(HH); free(cc); free(ss); free(grs); free(lhh);
   return 0;
 }
 
@@ -898,7 +914,7 @@ API int orc_solve(const orc_config *c, orc_result *res, double *x_out) {
     }
     if (minim == 0) for (int K = 0; K < G; K++) update_rhs(&B[K]); /* …multisplitting.c:164 */
     int done = 0;
-    while (!done && res->outer_its < max_outer) {
+    while (!done && res->outer_its < max_outer && !(c->max_seconds > 0.0 && now_s() - t_start >= c->max_seconds)) {
       if (minim == 0) {
         /* …multisplitting.c:170-206 */
         for (int K = 0; K < G; K++) { int it = inner_solve(c, &B[K]); if (K == 0) res->inner_its_total += it; }
@@ -908,6 +924,7 @@ API int orc_solve(const orc_config *c, orc_result *res, double *x_out) {
         double norm = sqrt(acc);
         res->last_norm = norm; push_hist(res, norm);
         if (norm <= thr_global) done = 1;
+        if (res->outer_its < 256) res->t_outer[res->outer_its] = now_s() - t_start;
         res->outer_its++;
         continue;
       }
@@ -974,6 +991,7 @@ API int orc_solve(const orc_config *c, orc_result *res, double *x_out) {
         res->last_norm = worst; push_hist(res, worst);
         if (all) done = 1;
       }
+      if (res->outer_its < 256) res->t_outer[res->outer_its] = now_s() - t_start;
       res->outer_its++;
     }
   } else {
@@ -1112,6 +1130,7 @@ API int orc_solve(const orc_config *c, orc_result *res, double *x_out) {
   }
   if (x_out) for (int K = 0; K < G; K++) memcpy(x_out + B[K].off, B[K].view + B[K].off, sizeof(double) * nb);
   for (int K = 0; K < G; K++) blk_free(&B[K]);
+  orc_gmres_release_workspace();
   free(B); free(S); free(R); free(alpha); free(bglob); free(xmin);
   return rc;
 }

@@ -92,6 +92,7 @@ typedef struct {
   /* async schedule (oracle simulation only): block K runs one step at tick t iff t % period[K] == 0 */
   int period[16];
   int nthreads;      /* OpenMP threads for elementwise loops (0 = leave) */
+  double max_seconds; /* synchronous drivers: leave the outer loop once it has run this long (0 = no cap; bench.py's CPU arm) */
 } orc_config;
 
 typedef struct {
@@ -108,6 +109,7 @@ typedef struct {
   int gmres_reason;
   double gmres_rnorm;
   double elapsed_s;         /* wall-clock of the outer loop only (the reference's MPI_Wtime region) */
+  double t_outer[256];      /* synchronous drivers: seconds since the start of the outer loop at the end of outer iteration i (i < 256) */
 } orc_result;
 
 /* ---- assembly (bit-exact gate) ---- */
@@ -133,6 +135,7 @@ double orc_block_residual_norm(int nrows, const int32_t *rowptr, const int32_t *
 
 /* ---- Krylov solvers ---- */
 void orc_ksp_defaults(orc_ksp_opts *o);
+void orc_gmres_release_workspace(void); /* the Krylov basis is kept between orc_gmres calls of the same size */
 int orc_gmres(int n, const int32_t *rowptr, const int32_t *colidx, const double *val, const double *b, double *x,
               const orc_ksp_opts *o, int *its, int *reason, double *rnorm, double *hist, int hist_cap);
 int orc_lsqr(int64_t nrows, int s, const double *R, int64_t ldr, const double *b, double *alpha, const orc_outer_opts *o,

@@ -45,7 +45,7 @@ class Config(C.Structure):
         ("alg", C.c_int), ("dim", C.c_int), ("m", C.c_int), ("n", C.c_int), ("p", C.c_int),
         ("nblocks", C.c_int), ("s", C.c_int), ("rtol", C.c_double),
         ("inner", KspOpts), ("outer", OuterOpts), ("max_outer", C.c_int),
-        ("period", C.c_int * 16), ("nthreads", C.c_int),
+        ("period", C.c_int * 16), ("nthreads", C.c_int), ("max_seconds", C.c_double),
     ]
 
 
@@ -55,6 +55,7 @@ class Result(C.Structure):
         ("norm0", C.c_double), ("last_norm", C.c_double), ("final_residual", C.c_double),
         ("error", C.c_double), ("hist_len", C.c_int), ("hist", C.c_double * 4096),
         ("gmres_its", C.c_int), ("gmres_reason", C.c_int), ("gmres_rnorm", C.c_double), ("elapsed_s", C.c_double),
+        ("t_outer", C.c_double * 256),
     ]
 
 
@@ -232,7 +233,7 @@ def lstsq_qr(R, b):
 
 # ---------------------------------------------------------------- outer loops
 def solve(alg, m, n, p=1, nblocks=2, s=4, rtol=1e-6, inner=None, outer_type="qr", outer_max_it=100,
-          outer_rtol=1e-15, max_outer=0, periods=None, nthreads=0, want_x=True):
+          outer_rtol=1e-15, max_outer=0, periods=None, nthreads=0, want_x=True, max_seconds=0.0):
     """Run one of the reference's drivers on the oracle.  ``inner`` is a dict of KspOpts fields."""
     cfg = Config()
     cfg.alg = ALG[alg] if isinstance(alg, str) else int(alg)
@@ -245,6 +246,7 @@ def solve(alg, m, n, p=1, nblocks=2, s=4, rtol=1e-6, inner=None, outer_type="qr"
     for i in range(16):
         cfg.period[i] = (periods[i] if periods and i < len(periods) else 1)
     cfg.nthreads = nthreads
+    cfg.max_seconds = max_seconds
     res = Result()
     ntot = m * n * max(p, 1)
     x = np.zeros(ntot) if want_x else None
@@ -255,7 +257,7 @@ def solve(alg, m, n, p=1, nblocks=2, s=4, rtol=1e-6, inner=None, outer_type="qr"
         "final_residual": res.final_residual, "error": res.error,
         "hist": np.array(res.hist[: res.hist_len]),
         "gmres_its": res.gmres_its, "gmres_reason": res.gmres_reason, "gmres_rnorm": res.gmres_rnorm, "x": x,
-        "elapsed_s": res.elapsed_s,
+        "elapsed_s": res.elapsed_s, "t_outer": list(res.t_outer)[: min(res.outer_its, 256)],
     }
     return out
 
