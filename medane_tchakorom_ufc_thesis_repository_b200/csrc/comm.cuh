@@ -9,6 +9,9 @@ struct Comm {
   // in-place sum over ranks of n doubles in device memory, result on every rank, stream ordered
   virtual int allreduce_sum(double *dbuf, int n, cudaStream_t st) = 0;
   virtual int barrier(cudaStream_t st) = 0;
+  // true: every block has its own stream on its own GPU/process, so a stream may wait on a word its neighbour writes
+  // (the in-process group of the tests serialises through host threads and keeps the barrier)
+  virtual bool neighbour_flags() const { return false; }
 };
 
 struct SelfComm : Comm {
@@ -111,5 +114,6 @@ struct NcclComm : Comm {
     if (!scratch) { CK(cudaMalloc(&scratch, 64)); CK(cudaMemsetAsync(scratch, 0, 64, st)); }
     return allreduce_sum(scratch, 1, st);
   }
+  bool neighbour_flags() const override { return true; }
 };
 

@@ -5,9 +5,23 @@
 // ------------------------------------------------------------------------------------------------
 static int exchange_sync(msp_engine *e) {
   // the boundary layers were already stored into the neighbours' windows by k_update_x / k_publish_boundary
-  // (class 3 of the profile = barrier + collection of the received layers; bytes = what crossed NVLink into this block)
+  // (class 3 of the profile = synchronisation + collection of the received layers; bytes = what crossed NVLink into this block)
   e->prof_begin(3, 8.0 * e->H * ((e->has_nb[0] ? 1 : 0) + (e->has_nb[1] ? 1 : 0)));
-  int rc = e->comm->barrier(e->st);
+  int rc = 0;
+  StreamWaitValue64Fn wait = e->comm->neighbour_flags() ? stream_wait_value64() : nullptr;
+  if (wait) {
+    // neighbour-only synchronisation: publish my sequence number to K-1 / K+1, wait for theirs (no collective)
+    const unsigned long long seq = ++e->ex_seq;
+    unsigned long long *f_lo = e->peer[0].base ? e->peer[0].flags() + 1 : nullptr; // I am the lower block's upper neighbour
+    unsigned long long *f_hi = e->peer[1].base ? e->peer[1].flags() + 0 : nullptr;
+    if (f_lo || f_hi) { k_signal_neighbours<<<1, 32, 0, e->st>>>(f_lo, f_hi, seq); e->launches++; }
+    for (int side = 0; side < 2 && !rc; side++)
+      if (e->has_nb[side] && wait(e->st, (unsigned long long)(uintptr_t)(e->win.flags() + side), seq, 0 /* CU_STREAM_WAIT_VALUE_GEQ */) != 0) {
+        g_err = "cuStreamWaitValue64 failed"; rc = 1;
+      }
+  } else {
+    rc = e->comm->barrier(e->st);
+  }
   if (!rc) rc = op_collect_halos(e);
   e->prof_end();
   return rc;
@@ -103,6 +117,7 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
   CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
   CK(cudaEventRecord(ev.a, e->st));
   const int64_t launches0 = e->launches;
+  CK(cudaMemsetAsync(reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, its_total), 0, sizeof(long long), e->st));
   e->prof = o->profile != 0;
   struct ProfOff { msp_engine *e; ~ProfOff() { e->prof = false; } } prof_off{e};
   bool done = false, time_up = false;
@@ -118,12 +133,10 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
   if (alg == MSP_ALG_SM) RC(op_update_rhs(e)); // …multisplitting.c:164
   while (!done && !time_up && res->outer_its < max_outer) {
     if (alg == MSP_ALG_SM) {
-      int its = 0, reason = 0;
       auto t0 = clk::now();
-      RC(op_inner_solve(e, &in, true, &its, &reason, nullptr));
+      RC(op_inner_solve(e, &in, true, nullptr, nullptr, nullptr, !e->prof));
       auto t1 = clk::now();
       res->stage_inner_s += secs(t0, t1);
-      res->inner_its_total += its;
       RC(exchange_sync(e));
       RC(op_update_rhs(e));
       RC(op_resid_sumsq(e, false, 0));
@@ -141,11 +154,9 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
     double inner_this = 0.0;
     for (int t = 0; t < s; t++) {
       RC(op_update_rhs(e));
-      int its = 0, reason = 0;
       auto t0 = clk::now();
-      RC(op_inner_solve(e, &in, true, &its, &reason, nullptr));
+      RC(op_inner_solve(e, &in, true, nullptr, nullptr, nullptr, !e->prof));
       inner_this += secs(t0, clk::now());
-      res->inner_its_total += its;
       RC(exchange_sync(e));
       RC(op_push_iterate(e, t));
     }
@@ -192,6 +203,11 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
   CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
   res->elapsed_s = ms * 1e-3;
   res->kernel_launches = e->launches - launches0;
+  {
+    long long tot = 0;
+    CK(cudaMemcpy(&tot, reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, its_total), sizeof(long long), cudaMemcpyDeviceToHost));
+    res->inner_its_total = tot;
+  }
   e->prof_collect(res);
   e->prof = false;
   // closing exchange + true residual + error (comm_sync_send_and_receive_final comm.c:199, utils.c:575, :1045)

@@ -52,6 +52,19 @@ static inline int grid_for(long long work_items, int per_sm = 8) {
 
 #include "comm.cuh"
 
+// cuStreamWaitValue64 through the runtime's driver entry-point query (no link against libcuda)
+typedef int (*StreamWaitValue64Fn)(cudaStream_t, unsigned long long, unsigned long long, unsigned int);
+static StreamWaitValue64Fn stream_wait_value64() {
+  static StreamWaitValue64Fn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (getenv("MSPLIT_NO_FLAGS") != nullptr) return (StreamWaitValue64Fn) nullptr;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); p = nullptr; }
+    return (StreamWaitValue64Fn)p;
+  }();
+  return fn;
+}
+
 // ------------------------------------------------------------------------------------------------
 // engine
 // ------------------------------------------------------------------------------------------------
@@ -69,6 +82,8 @@ struct Window {
   AsyncHdrDev *hdr(int side) const { return reinterpret_cast<AsyncHdrDev *>(base + (size_t)4 * H) + side; }
   CdMailbox *mailbox() const { return reinterpret_cast<CdMailbox *>(base + (size_t)4 * H + 8); }
   double *factor(int J) const { return base + (size_t)4 * H + 8 + 16 + (size_t)J * fslot; }
+  // [0]: exchange sequence number published by the lower neighbour, [1]: by the upper neighbour (the 8 spare doubles at the end)
+  unsigned long long *flags() const { return reinterpret_cast<unsigned long long *>(base + (size_t)4 * H + 8 + 16 + (size_t)G * fslot); }
   static int fslot_for(int smax) { return (smax + 1) * (smax + 1) + 2; }
   static size_t size_for(int H, int G, int smax) { return sizeof(double) * ((size_t)4 * H + 8 + 16 + (size_t)G * fslot_for(smax) + 8); }
 };
@@ -112,6 +127,7 @@ struct msp_engine {
   std::vector<double> fcache; // newest valid factor seen from each block [G x fslot]
   std::vector<int> fcache_seq;
   int par = 0;
+  unsigned long long ex_seq = 0; // synchronous exchanges done (neighbour-flag protocol)
   Comm *comm = nullptr;
   bool own_comm = false;
   CdState *cd = nullptr;
@@ -504,8 +520,8 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   }
   dalloc(&e->ws.partial, sizeof(double) * (size_t)MSPK_MAX_PART * 8 * 24);
   dalloc(&e->dsc, sizeof(double) * 256);
-  dalloc(&e->dfac, sizeof(double) * (size_t)p->nblocks * (e->smax + 1) * (e->smax + 1) + 64);
-  if (e->smax > 0) dalloc(&e->gram_partial, sizeof(double) * 45 * MSPK_MAX_PART);
+  dalloc(&e->dfac, sizeof(double) * ((size_t)p->nblocks + 1) * (e->smax + 1) * (e->smax + 1) + 64);
+  if (e->smax > 0) dalloc(&e->gram_partial, sizeof(double) * 64 * MSPK_MAX_PART);
   e->use_cholqr = getenv("MSPLIT_NO_CHOLQR") == nullptr;
   e->win.H = e->H; e->win.G = p->nblocks; e->win.fslot = Window::fslot_for(e->smax);
   e->win.bytes = Window::size_for(e->H, p->nblocks, e->smax);

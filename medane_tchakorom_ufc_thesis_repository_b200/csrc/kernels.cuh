@@ -38,6 +38,7 @@ struct GmresCtl {
   int refine;      // second CGS pass requested (REFINE_IFNEEDED)
   int first_cycle; // ksp->rnorm == -1 marker
   int pad0;
+  long long its_total; // sum of KSPGetIterationNumber over the inner solves since the driver cleared it (read once per solve)
   double res;      // current recurrence residual
   double ksp_rnorm;
   double gm_rnorm0; // residual at the start of the cycle
@@ -970,6 +971,7 @@ __global__ void k_build_soln_coef(GmresCtl *c) {
   const int ld = MSPK_MAXK + 2;
   const int k1 = c->it - 1;
   if (k1 < 0) return;
+  c->its_total += c->it;
   bool bad = false;
   if (c->hh[(size_t)k1 * ld + k1] != 0.0) c->nrs[k1] = c->grs[k1] / c->hh[(size_t)k1 * ld + k1];
   else bad = true;
@@ -1018,6 +1020,18 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_update_x(UpdateXArgs a) {
     if (a.peer_lo && r < a.H) a.peer_lo[r] = xv;
     if (a.peer_hi && r >= a.nb - a.H) a.peer_hi[r - (a.nb - a.H)] = xv;
   }
+}
+
+// synchronous exchange without a global barrier: after its boundary layers are stored, a block publishes the exchange
+// sequence number into each neighbour's window (release: the layers are visible before the number); the neighbour's
+// stream waits on that word (cuStreamWaitValue64, no kernel spins) before it collects the layers.  Only blocks K-1 / K+1
+// ever wait for block K — replaces the MPI_Sendrecv pairing of comm.c:135 (and round 1's NCCL allreduce barrier).
+__global__ void k_signal_neighbours(unsigned long long *flag_lo, unsigned long long *flag_hi, unsigned long long seq) {
+  if (threadIdx.x || blockIdx.x) return;
+  __threadfence_system();
+  if (flag_lo) *reinterpret_cast<volatile unsigned long long *>(flag_lo) = seq;
+  if (flag_hi) *reinterpret_cast<volatile unsigned long long *>(flag_hi) = seq;
+  __threadfence_system();
 }
 
 // publish only the boundary layers (used after the minimisation rewrote x, and by the closing exchange)
@@ -1212,6 +1226,107 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_right_trsolve(int nb, long lon
       y[j] = t * rinv[j];
     }
     for (int c = 0; c < NC; c++) C[c * ld + r] = y[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wide bases (s + 1 > 9 columns: the reference's s = 10 and s = 20 runs): the same CholeskyQR2, blocked in panels of
+// <= 8 columns.  k_gram_panel contracts two panels (<= 8 x 8 inner products, 64 accumulators in registers, one pass over
+// the <= 16 columns); k_apply_upper multiplies by the inverse Cholesky factor panel by panel, in place, last panel first
+// (output panel j only needs the input panels <= j).  Bytes for 21 columns: 3 diagonal + 3 off-diagonal panel pairs =
+// 576 n per Gram, 576 n per application, against ~8 000 n for Gram-Schmidt with reorthogonalisation column by column.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MSPK_THREADS) k_gram_panel(int nb, long long ld, const double *__restrict__ A, int na, const double *__restrict__ B, int nbc,
+                                                             double *partial /* [64 x MSPK_MAX_PART] */, unsigned int *counter,
+                                                             double *out, int ldo /* out[(b) * ldo + a] = <A_a, B_b> */) {
+  double acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 8; b++) acc[a][b] = 0.0;
+  const long long npairs = nb >> 1;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npairs; p += (long long)gridDim.x * blockDim.x) {
+    double2 va[8], vb[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) va[a] = (a < na) ? ld_stream2(A + a * ld + 2 * p) : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int b = 0; b < 8; b++) vb[b] = (b < nbc) ? ld_stream2(B + b * ld + 2 * p) : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+      for (int b = 0; b < 8; b++) acc[a][b] = fma(va[a].y, vb[b].y, fma(va[a].x, vb[b].x, acc[a][b]));
+  }
+  if ((nb & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int a = 0; a < na; a++)
+      for (int b = 0; b < nbc; b++) acc[a][b] = fma(A[a * ld + nb - 1], B[b * ld + nb - 1], acc[a][b]);
+  }
+  __shared__ double sm[32];
+  __shared__ bool last;
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      if (a < na && b < nbc) { // uniform over the block
+        double bs = block_sum(acc[a][b], sm);
+        if (threadIdx.x == 0) partial[(long long)(a * 8 + b) * MSPK_MAX_PART + blockIdx.x] = bs;
+      }
+    }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned q = atomicAdd(counter, 1u);
+    last = (q == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    for (int a = 0; a < na; a++)
+      for (int b = 0; b < nbc; b++) {
+        double v = 0.0;
+        for (int k = threadIdx.x; k < gridDim.x; k += blockDim.x) v += __ldcg(partial + (long long)(a * 8 + b) * MSPK_MAX_PART + k);
+        double tot = block_sum(v, sm);
+        if (threadIdx.x == 0) out[(long long)b * ldo + a] = tot;
+      }
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+// C[:, j0 .. j0+wj) := sum_{i < j0+wj} C[:, i] * T[i, j] for an upper-triangular T (nc x nc, column-major): in place,
+// called for the LAST panel first.  T lives in shared memory (nc <= 33: 8.7 KB).
+__global__ void __launch_bounds__(MSPK_THREADS) k_apply_upper(int nb, long long ld, double *__restrict__ C, int nc, int j0, int wj, const double *__restrict__ T) {
+  extern __shared__ double t_sm[];
+  for (int i = threadIdx.x; i < nc * nc; i += blockDim.x) t_sm[i] = T[i];
+  __syncthreads();
+  const long long npairs = nb >> 1;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npairs; p += (long long)gridDim.x * blockDim.x) {
+    double2 acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) acc[c] = make_double2(0.0, 0.0);
+    for (int i0 = 0; i0 < j0 + wj; i0 += 8) {
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = (i0 + u < j0 + wj) ? ld_stream2(C + (long long)(i0 + u) * ld + 2 * p) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+          if (c < wj && i0 + u <= j0 + c) {
+            const double t = t_sm[(j0 + c) * nc + i0 + u];
+            acc[c].x = fma(v[u].x, t, acc[c].x); acc[c].y = fma(v[u].y, t, acc[c].y);
+          }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+      if (c < wj) __stcs(reinterpret_cast<double2 *>(C + (long long)(j0 + c) * ld + 2 * p), acc[c]);
+  }
+  if ((nb & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long r = nb - 1;
+    double acc[8];
+    for (int c = 0; c < wj; c++) {
+      double t = 0.0;
+      for (int i = 0; i <= j0 + c; i++) t = fma(C[(long long)i * ld + r], t_sm[(j0 + c) * nc + i], t);
+      acc[c] = t;
+    }
+    for (int c = 0; c < wj; c++) C[(long long)(j0 + c) * ld + r] = acc[c];
   }
 }
 

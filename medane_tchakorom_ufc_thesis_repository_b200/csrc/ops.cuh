@@ -34,7 +34,11 @@ static int read_scalars(msp_engine *e, int first, int n) {
 
 // inner_solver utils.c:950-970 -> KSPSolve_GMRES.  One host synchronisation per
 // restart cycle; inside a cycle every decision is taken on the device.
-static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, int *its_out, int *reason_out, double *rnorm_out) {
+// `defer`: when the solve is known to be ONE restart cycle (max_it <= restart) and the caller does not ask for
+// its / reason / rnorm, nothing is read back and the host does not wait: the cycle's kernels decide everything on the
+// device, its iteration count is added to ctl->its_total, and the caller's next stream synchronisation covers it.
+static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, int *its_out, int *reason_out, double *rnorm_out, bool defer = false) {
+  defer = defer && !its_out && !reason_out && !rnorm_out && o->max_it <= o->restart;
   if (o->restart < 1 || o->restart > e->prob.max_restart) MSP_FAIL("restart exceeds max_restart of the engine");
   const bool guess_zero = !o->guess_nonzero;
   double *bnorm_sq = nullptr;
@@ -133,6 +137,7 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
       RC(enqueue_cycle());
     }
     first = false;
+    if (defer) return 0;
     CK(cudaStreamSynchronize(e->st));
     memcpy(&hc, e->hsc + 32, 16);
     itcount += hc.it;
@@ -273,6 +278,38 @@ static void launch_trsolve(msp_engine *e, int nc, double *C, const double *U_dev
   }
 }
 
+// Gram matrix of nc > 9 columns at C, panel by panel, upper triangle into out_dev (nc x nc column-major)
+static void launch_gram_wide(msp_engine *e, int nc, const double *C, double *out_dev) {
+  const int grid = grid_for((long long)e->nb / 2, std::min(resident_blocks_per_sm(k_gram_panel), 4));
+  for (int j0 = 0; j0 < nc; j0 += 8)
+    for (int i0 = 0; i0 <= j0; i0 += 8) {
+      k_gram_panel<<<grid, MSPK_THREADS, 0, e->st>>>(e->nb, e->ld, C + (long long)i0 * e->ld, std::min(8, nc - i0), C + (long long)j0 * e->ld, std::min(8, nc - j0),
+                                                     e->gram_partial, e->ws.counter + MSPK_GRAM_COUNTER, out_dev + (long long)j0 * nc + i0, nc);
+      e->launches++;
+    }
+}
+// C := C T for an upper-triangular T (device, nc x nc), in place, last panel first
+static void launch_apply_upper(msp_engine *e, int nc, double *C, const double *T_dev) {
+  const int grid = grid_for((long long)e->nb / 2, std::min(resident_blocks_per_sm(k_apply_upper), 4));
+  const int last0 = ((nc - 1) / 8) * 8;
+  for (int j0 = last0; j0 >= 0; j0 -= 8) {
+    k_apply_upper<<<grid, MSPK_THREADS, sizeof(double) * nc * nc, e->st>>>(e->nb, e->ld, C, nc, j0, std::min(8, nc - j0), T_dev);
+    e->launches++;
+  }
+}
+// inverse of an upper-triangular matrix (column-major, host)
+static void upper_inverse(int nc, const double *U, double *T) {
+  std::fill(T, T + (size_t)nc * nc, 0.0);
+  for (int j = 0; j < nc; j++) {
+    T[(size_t)j * nc + j] = 1.0 / U[(size_t)j * nc + j];
+    for (int i = j - 1; i >= 0; i--) {
+      double t = 0.0;
+      for (int k = i + 1; k <= j; k++) t += U[(size_t)k * nc + i] * T[(size_t)j * nc + k];
+      T[(size_t)j * nc + i] = -t / U[(size_t)i * nc + i];
+    }
+  }
+}
+
 // CGS2 leaf (classical Gram-Schmidt with reorthogonalisation, the Arnoldi kernels K3, K4+K5) on the nc columns at e->R
 static int local_qr_cgs2(msp_engine *e, int nc, std::vector<double> &U) {
   U.assign((size_t)nc * nc, 0.0);
@@ -308,17 +345,27 @@ static int op_local_qr(msp_engine *e, int kind, int s, double *u_aug /* host (s+
   e->launches++;
   std::vector<double> U, U1, U2, G((size_t)nc * nc, 0.0);
   bool have_u1 = false;
-  if (e->use_cholqr && nc >= 2 && nc <= 9) {
+  if (e->use_cholqr && nc >= 2 && nc <= MSP_MAX_S + 1) {
+    // nc <= 9: one register-resident Gram kernel and a triangular solve; wider bases: the same in panels of 8 columns,
+    // with the inverse factor applied as a product
+    const bool wide = nc > 9;
+    std::vector<double> T((size_t)nc * nc);
     U1.assign((size_t)nc * nc, 0.0); U2.assign((size_t)nc * nc, 0.0);
-    double *Gdev = e->dfac; // idle between TSQR gathers; (smax+1)^2 doubles fit
-    launch_gram(e, nc, e->R, Gdev);
+    double *Gdev = e->dfac + (size_t)e->prob.nblocks * nc * nc; // behind the G factor slots of the TSQR gather
+    if (wide) launch_gram_wide(e, nc, e->R, Gdev); else launch_gram(e, nc, e->R, Gdev);
     CK(cudaMemcpyAsync(G.data(), Gdev, sizeof(double) * nc * nc, cudaMemcpyDeviceToHost, e->st));
     CK(cudaStreamSynchronize(e->st));
     if (chol_upper(nc, G.data(), U1.data())) {
-      CK(cudaMemcpyAsync(Gdev, U1.data(), sizeof(double) * nc * nc, cudaMemcpyHostToDevice, e->st));
-      launch_trsolve(e, nc, e->R, Gdev);
+      if (wide) {
+        upper_inverse(nc, U1.data(), T.data());
+        CK(cudaMemcpyAsync(Gdev, T.data(), sizeof(double) * nc * nc, cudaMemcpyHostToDevice, e->st));
+        launch_apply_upper(e, nc, e->R, Gdev);
+      } else {
+        CK(cudaMemcpyAsync(Gdev, U1.data(), sizeof(double) * nc * nc, cudaMemcpyHostToDevice, e->st));
+        launch_trsolve(e, nc, e->R, Gdev);
+      }
       have_u1 = true;
-      launch_gram(e, nc, e->R, Gdev);
+      if (wide) launch_gram_wide(e, nc, e->R, Gdev); else launch_gram(e, nc, e->R, Gdev);
       CK(cudaMemcpyAsync(G.data(), Gdev, sizeof(double) * nc * nc, cudaMemcpyDeviceToHost, e->st));
       CK(cudaStreamSynchronize(e->st));
       if (chol_upper(nc, G.data(), U2.data())) {

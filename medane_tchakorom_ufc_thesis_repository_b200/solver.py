@@ -193,6 +193,51 @@ class Engine:
         check(_lib.lib().msp_apply_alpha(self.h, ALG[kind] if isinstance(kind, str) else kind,
                                          np.ascontiguousarray(alpha, np.float64)))
 
+    # ---- the exchange and the minimiser as separate calls (include/comm.h, include/utils.h of the reference)
+    def connect_local(self, side, neighbour: "Engine"):
+        """Wire a neighbour engine of the same process (side 0: block K-1, side 1: block K+1)."""
+        check(_lib.lib().msp_connect_local(self.h, side, neighbour.h))
+
+    def compute_rhs_ones(self):
+        """computeTheRightHandSideWithInitialGuess utils.c:623-650: b_K = A_K,: 1, rhs_K = b_K, halos zero."""
+        check(_lib.lib().msp_compute_rhs_ones(self.h))
+
+    def comm_sync_send_and_receive(self):
+        """comm.c:126-141 (collective: one caller per block)."""
+        check(_lib.lib().msp_exchange_sync(self.h))
+
+    def async_reset(self):
+        check(_lib.lib().msp_async_reset(self.h))
+
+    def comm_async_test_and_send(self, iteration):
+        """comm.c:531-554."""
+        check(_lib.lib().msp_exchange_async_publish(self.h, iteration))
+
+    def comm_async_probe_and_receive(self):
+        """comm.c:455-529; returns [accepted_lower, accepted_upper]."""
+        acc = (C.c_int * 2)()
+        check(_lib.lib().msp_exchange_async_poll(self.h, acc))
+        return [int(acc[0]), int(acc[1])]
+
+    def outer_solver_norm_equation(self, kind, outer_type="tsqr", outer_max_it=100, outer_rtol=1e-15):
+        """utils.c:1061-1103 (+ the outer-solver menu utils.c:972-1043): returns (alpha, ||rhs - R alpha||); x = S alpha is applied."""
+        alpha = np.zeros(self.s)
+        rn = C.c_double()
+        ot = {"tsqr": 0, "qr": 0, "lsqr": 1, "gram": 2, "normal": 2, "cg": 3, "cgne": 4}[outer_type]
+        check(_lib.lib().msp_minimize(self.h, ALG[kind] if isinstance(kind, str) else kind, ot, outer_max_it, outer_rtol, alpha, C.byref(rn)))
+        return alpha, rn.value
+
+    def computeFinalResidualNorm(self):
+        """utils.c:575-595 (collective)."""
+        out = C.c_double()
+        check(_lib.lib().msp_residual_norm(self.h, C.byref(out)))
+        return out.value
+
+    def get_solution(self):
+        out = np.empty(self.nb, np.float64)
+        check(_lib.lib().msp_get_solution(self.h, out))
+        return out
+
     # raw kernels on host data
     def spmv(self, which, x, halo_lo=None, halo_hi=None):
         y = np.empty(self.nb)

@@ -354,6 +354,53 @@ def test_tsqr_minimisation_matches_lstsq(S, oracle):
         e.close()
 
 
+@pytest.mark.parametrize("m,n,G,s", [(24, 16, 2, 10), (21, 15, 3, 20), (33, 7, 1, 12), (40, 24, 2, 32)])
+def test_wide_basis_panel_cholqr_matches_lstsq(S, oracle, m, n, G, s):
+    """s + 1 > 9 columns (the reference's s = 10 / 20 runs): CholeskyQR2 blocked in panels of 8 columns (k_gram_panel,
+    k_apply_upper) against an exact least squares on the whole grid; odd block sizes exercise the scalar tails."""
+    rng = np.random.default_rng(5)
+    factors, blocks = [], []
+    Sg = rng.standard_normal((s, m * n))
+    for K in range(G):
+        e = S.Engine(m, n, block=K, nblocks=G, s=s)
+        nb, H = e.nb, e.H
+        off = K * nb
+        for t in range(s):
+            e.x = Sg[t, off:off + nb]
+            if K > 0: e.set_halo(0, Sg[t, off - H:off])
+            if K < G - 1: e.set_halo(1, Sg[t, off + nb:off + nb + H])
+            e.push_iterate(t)
+        e.spmm_AS("SMSM_GLOBAL")
+        factors.append(e.minimize_local_qr("SMSM_GLOBAL"))
+        blocks.append(e)
+    alpha, rn = S.tsqr_combine(s, factors)
+    A = oracle.poisson2d(m, n, 0, 1)
+    R = np.stack([oracle.spmv(*A, Sg[t]) for t in range(s)], axis=1)
+    b = oracle.spmv(*A, np.ones(m * n))
+    a_ref, rn_ref = oracle.lstsq_qr(R, b)
+    alpha_raw = alpha - np.append(alpha[1:], 0.0)
+    assert np.allclose(alpha_raw, a_ref, rtol=1e-8, atol=1e-10)
+    assert abs(rn - rn_ref) <= 1e-10 * rn_ref
+    # same factor (up to column signs) from the Gram-Schmidt fallback
+    os.environ["MSPLIT_NO_CHOLQR"] = "1"
+    try:
+        e2 = S.Engine(m, n, block=0, nblocks=G, s=s)
+    finally:
+        del os.environ["MSPLIT_NO_CHOLQR"]
+    nb, H = e2.nb, e2.H
+    for t in range(s):
+        e2.x = Sg[t, :nb]
+        if G > 1: e2.set_halo(1, Sg[t, nb:nb + H])
+        e2.push_iterate(t)
+    e2.spmm_AS("SMSM_GLOBAL")
+    u_gs = np.array(e2.minimize_local_qr("SMSM_GLOBAL")).reshape(s + 1, s + 1)
+    u_ch = np.array(factors[0]).reshape(s + 1, s + 1)
+    assert np.allclose(np.abs(u_gs), np.abs(u_ch), rtol=1e-7, atol=1e-9 * np.abs(u_ch).max())
+    e2.close()
+    for e in blocks:
+        e.close()
+
+
 # ------------------------------------------------------------------ whole drivers, all blocks in one process on one GPU
 def _golden_runs():
     with open(os.path.join(GOLD, "oracle_sync_runs.json")) as f:
@@ -635,22 +682,31 @@ def test_cholqr_breakdown_falls_back(S, oracle):
 def test_operator_surface_hand_driven(S, oracle):
     """The fine-grained operator surface (updateLocalRHS, inner_solver, the exchange, MatMatMult, the minimiser) driven
     from the host exactly like the reference's main() does (…-minimization-global.c:288-363), against the fused
-    msp_group_solve loop and the oracle: same iterates."""
+    msp_group_solve loop and the oracle: same iterates.  The boundary layers move DEVICE TO DEVICE: the two engines are
+    wired as neighbours and use the asynchronous publish / poll pair (one host thread, so the collective
+    comm_sync_send_and_receive cannot be used here; it is covered by the threaded test below)."""
     m, n, G, s = 32, 24, 2, 3
     inner = dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)
     ko = S.ksp_opts(**inner)
     blocks = [S.Engine(m, n, block=k, nblocks=G, s=s, max_restart=30) for k in range(G)]
-    H = blocks[0].H
+    blocks[0].connect_local(1, blocks[1])
+    blocks[1].connect_local(0, blocks[0])
+    for e in blocks:
+        e.async_reset()
     norm0 = np.sqrt(sum(np.linalg.norm(e.b) ** 2 for e in blocks))
     hist = []
+    step = 0
     for outer in range(3):
         for t in range(s):
             for e in blocks:
                 e.updateLocalRHS()
                 e.inner_solver(ko)
-            xs = [e.x for e in blocks]                       # comm_sync_send_and_receive: boundary layers only
-            blocks[0].set_halo(1, xs[1][:H])
-            blocks[1].set_halo(0, xs[0][-H:])
+            for e in blocks:
+                e.comm_async_test_and_send(step)               # P2P store of the layer + header release
+            got = [e.comm_async_probe_and_receive() for e in blocks]
+            assert got == [[0, 1], [1, 0]]                      # every block took its one neighbour's new layer
+            assert blocks[0].comm_async_probe_and_receive() == [0, 0]   # nothing newer: no second copy
+            step += 1
             for e in blocks:
                 e.push_iterate(t)
         for e in blocks:
@@ -660,7 +716,7 @@ def test_operator_surface_hand_driven(S, oracle):
         for e in blocks:
             e.apply_alpha("SMSM_GLOBAL", alpha)
         hist.append(rn)
-    x_hand = np.concatenate([e.x for e in blocks])
+    x_hand = np.concatenate([e.get_solution() for e in blocks])
     for e in blocks:
         e.close()
     grp = S.Group(m, n, nblocks=G, s=s, max_restart=30)
@@ -670,6 +726,138 @@ def test_operator_surface_hand_driven(S, oracle):
     assert np.linalg.norm(x_hand - grp.solution()) <= 1e-12 * np.linalg.norm(x_hand)
     assert np.linalg.norm(x_hand - ref["x"]) <= 1e-8 * np.linalg.norm(x_hand)
     assert abs(res[0]["norm0"] - norm0) <= 1e-12 * norm0
+    grp.close()
+
+
+@pytest.mark.parametrize("kind,outer_type", [("SMSM_GLOBAL", "tsqr"), ("SMSM_SEMI_LOCAL", "tsqr"), ("SMSM_LOCAL", "tsqr")])
+def test_collective_surface_one_thread_per_block(S, oracle, kind, outer_type):
+    """comm_sync_send_and_receive (msp_exchange_sync), the one-call minimiser (msp_minimize) and computeFinalResidualNorm
+    (msp_residual_norm) are collectives: one host thread per block drives the reference's loop
+    (…-global.c:288-363, …-semi-local.c:278-347, …-local.c:224-280) call by call; the iterates must equal the fused
+    driver's and the oracle's."""
+    import threading
+    m, n, G, s = 36, 20, 3, 4
+    inner = dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)
+    ko = S.ksp_opts(**inner)
+    grp = S.Group(m, n, nblocks=G, s=s, max_restart=30)
+    norms = [[] for _ in range(G)]
+    finals = [None] * G
+    errors = []
+
+    def body(k):
+        try:
+            e = grp.engines[k]
+            for outer in range(2):
+                for t in range(s):
+                    e.updateLocalRHS()
+                    e.inner_solver(ko)
+                    e.comm_sync_send_and_receive()
+                    e.push_iterate(t)
+                e.spmm_AS(kind)
+                if kind == "SMSM_LOCAL":
+                    e.updateLocalRHS()
+                alpha, rn = e.outer_solver_norm_equation(kind, outer_type=outer_type, outer_max_it=60)
+                norms[k].append(rn)
+            e.comm_sync_send_and_receive()
+            finals[k] = e.computeFinalResidualNorm()
+        except Exception as ex:  # pragma: no cover
+            errors.append(ex)
+
+    th = [threading.Thread(target=body, args=(k,)) for k in range(G)]
+    [t.start() for t in th]
+    [t.join(120) for t in th]
+    assert not errors, errors
+    x_hand = grp.solution()
+    ref = oracle.solve(kind, m, n, nblocks=G, s=s, rtol=1e-300, inner=inner, max_outer=2)
+    assert np.linalg.norm(x_hand - ref["x"]) <= 1e-8 * np.linalg.norm(ref["x"])
+    assert abs(finals[0] - ref["final_residual"]) <= 1e-8 * ref["final_residual"] and len(set(finals)) == 1
+    if kind == "SMSM_GLOBAL":
+        assert np.allclose(norms[0], ref["hist"], rtol=1e-7) and norms[0] == norms[1] == norms[2]
+    grp.close()
+
+
+@pytest.mark.parametrize("outer_type", ["cg", "cgne"])
+@pytest.mark.parametrize("alg,G", [("SMSM_GLOBAL", 2), ("SMSM_LOCAL", 2), ("SMSM_SEMI_LOCAL", 3)])
+def test_cg_and_cgne_minimisers(S, oracle, alg, G, outer_type):
+    """The rest of the reference's outer-solver menu: `outer_solver` = PETSc CG on the explicit normal
+    equations R'R alpha = R'b (utils.c:972-996, the default -outer_ksp_type cg of config/default_run_variables) and
+    `outer_solver_cgne` = CGNE on R (utils.c:1020-1043).  In exact arithmetic both end at the least-squares minimiser
+    after <= s steps; checked against the oracle's exact minimiser on a well-conditioned basis."""
+    inner = dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)
+    grp = S.Group(32, 30, nblocks=G, s=4, max_restart=30)
+    res = grp.solve(alg, s=4, rtol=1e-300, inner=S.ksp_opts(**inner), max_outer=2, outer_type=outer_type, outer_max_it=50, outer_rtol=1e-14)
+    ref = oracle.solve(alg, 32, 30, nblocks=G, s=4, rtol=1e-300, inner=inner, max_outer=2)
+    x = grp.solution()
+    assert np.linalg.norm(x - ref["x"]) <= 1e-6 * np.linalg.norm(ref["x"])
+    assert np.allclose(np.max([r["hist"] for r in res], axis=0), ref["hist"], rtol=1e-5)
+    assert 0 < res[0]["outer_solver_its"] <= 2 * 50
+    grp.close()
+
+
+def test_mgs_with_refinement_option_terminates(S, oracle):
+    """-ksp_gmres_modifiedgramschmidt together with a CGS refinement type (PETSc ignores the refinement under
+    MGS) used to spin forever; it must behave exactly like plain MGS."""
+    N = 24
+    e = S.Engine(N, N, max_restart=20)
+    r1 = e.gmres_solve(S.ksp_opts(restart=20, max_it=300, rtol=1e-8, abstol=1e-100, initial_rtol=1, mgs=1))
+    x1 = e.x
+    for refine in (1, 2):
+        r2 = e.gmres_solve(S.ksp_opts(restart=20, max_it=300, rtol=1e-8, abstol=1e-100, initial_rtol=1, mgs=1, cgs_refine=refine))
+        assert r2["gmres_its"] == r1["gmres_its"] and r2["gmres_reason"] == r1["gmres_reason"]
+        assert np.array_equal(e.x, x1)
+    e.close()
+
+
+def test_odd_block_on_plain_dia_view(S, oracle, monkeypatch):
+    """odd block sizes on the plain DIA kernel (coded view disabled): 3 blocks of a 9 x 7 grid."""
+    monkeypatch.setenv("MSPLIT_NO_CDIA", "1")
+    m, n, G = 9, 7, 3
+    rng = np.random.default_rng(2)
+    xg = rng.standard_normal(m * n)
+    for K in range(G):
+        e = S.Engine(m, n, block=K, nblocks=G, keep_csr=True)
+        assert e.spmv_format()[0] == "dia" and e.nb % 2 == 1
+        nb, H = e.nb, e.H
+        off = K * nb
+        lo = xg[off - H:off] if K > 0 else None
+        hi = xg[off + nb:off + nb + H] if K < G - 1 else None
+        y = e.spmv(S.MAT_STRIP, xg[off:off + nb], lo, hi)
+        rp, ci, va = oracle.poisson2d(m, n, K, G)
+        assert np.array_equal(y, oracle.spmv(rp, ci, va, xg))
+        e.close()
+
+
+def test_group_abort_reports_the_failing_block(S):
+    """a block-local failure must end the whole group call with that block's error instead of leaving the
+    other block threads waiting in a collective forever."""
+    import threading
+    grp = S.Group(16, 16, nblocks=2, s=9, max_restart=30)   # s = 9: the normal-equations minimiser (s <= 8) fails in every block
+    out = {}
+
+    def run():
+        try:
+            grp.solve("SMSM_GLOBAL", s=9, rtol=1e-6, inner=S.ksp_opts(restart=30, max_it=3, rtol=1e-10, abstol=1e-100), max_outer=5, outer_type="gram")
+            out["err"] = None
+        except S.MsplitError as ex:
+            out["err"] = str(ex)
+
+    t = threading.Thread(target=run)
+    t.start()
+    t.join(60)
+    assert not t.is_alive(), "group solve hung after a block failed"
+    assert out["err"] and "s <= 8" in out["err"]
+    # the group is usable afterwards
+    res = grp.solve("SMSM_GLOBAL", s=9, rtol=1e-6, inner=S.ksp_opts(restart=30, max_it=3, rtol=1e-10, abstol=1e-100), max_outer=2)
+    assert res[0]["outer_its"] == 2
+    grp.close()
+
+
+def test_wall_clock_cap(S):
+    """msp_solve_opts.max_seconds: all blocks leave at the same outer iteration, stop_reason says why."""
+    grp = S.Group(256, 256, nblocks=2, s=5, max_restart=30)
+    res = grp.solve("SMSM_GLOBAL", s=5, rtol=1e-30, inner=S.ksp_opts(restart=30, max_it=20, rtol=1e-10, abstol=1e-100), max_outer=100000, max_seconds=0.5)
+    assert res[0]["stop_reason"] == 2 and res[0]["outer_its"] == res[1]["outer_its"] > 0
+    assert res[0]["elapsed_s"] < 5.0
     grp.close()
 
 
@@ -733,6 +921,14 @@ def test_msolve_c_driver(S, oracle):
     fr = float(re.search(r"Final residual norm 2 = ([0-9.e+-]+)", out.stdout).group(1))
     assert fr <= 1e-6 * ref["norm0"] * 1.000001
     assert re.search(r"Erreur : [0-9.e+-]+", out.stdout)
+    # -log_view: the reference's two solve stages (…-global.c:81-89) and the flame-graph lines of tmp/function-calling-stack
+    st_in = float(re.search(r"Stage I_Solver \(inner GMRES solves\): ([0-9.]+) s", out.stdout).group(1))
+    st_out = float(re.search(r"Stage O_Solver \(exchange, A\*S, minimisation, convergence test\): ([0-9.]+) s", out.stdout).group(1))
+    assert st_in > 0 and st_out > 0
+    for ev in ("KSPSolve;KSPGMRESOrthog;VecMDot", "KSPSolve;KSPGMRESOrthog;VecMAXPY", "KSPSolve;MatMult"):
+        us = float(re.search(r"total solving;I_Solver stage;" + re.escape(ev) + r" ([0-9]+)", out.stdout).group(1))
+        assert us > 0
+    assert re.search(r"algorithmic GB/s: VecMDot [0-9]+", out.stdout)
     # stand-alone GMRES binary name + un-prefixed options (running_bulk_test_local:40-45)
     out = subprocess.run([exe, "-alg", "gmres_solution", "-m", "32", "-n", "32", "-ksp_type", "gmres", "-ksp_rtol", "1e-4", "-ksp_atol", "1e-100",
                           "-ksp_max_it", "1000000000", "-pc_type", "none", "-ksp_norm_type", "UNPRECONDITIONED",

@@ -41,6 +41,32 @@ for alg, m, n, p, s, rtol, inner in cases:
               f"resid {res['final_residual'] / res['norm0']:.3e}, elapsed {res['elapsed_s'] * 1e3:.1f} ms {'ok' if good else 'FAIL'}", flush=True)
     eng.close()
     D.barrier()
+# asynchronous variants, free-running across processes (no barrier inside the loop; NVLink-mapped headers, mailboxes and
+# TSQR-factor slots): judged on the true residual after the closing synchronous exchange (…-global_prime.c:503-516)
+async_cases = [
+    ("AM", 64, 64, 1, 0, 1e-5, dict(restart=30, max_it=20, rtol=1e-10, abstol=1e-100)),
+    ("AMAM_GLOBAL", 64, 64, 1, 5, 1e-6, dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)),
+    ("AMAM_SEMI_LOCAL", 64, 64, 1, 4, 1e-4, dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)),
+    ("AMAM_LOCAL", 64, 64, 1, 4, 1e-4, dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)),
+    ("AMAM_GLOBAL", 16, 16, 16, 5, 1e-6, dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)),
+]
+for alg, m, n, p, s, rtol, inner in async_cases:
+    eng = D.make_distributed_engine(m, n, p, s=max(s, 0), max_restart=30)
+    res = eng.solve(alg, s=s, rtol=rtol, inner=S.ksp_opts(**inner), max_outer=200000, max_seconds=60.0)
+    its_all = D.allgather_bytes(str(res["outer_its"]).encode())
+    if rank == 0:
+        rel = res["final_residual"] / res["norm0"]
+        # the detection protocol bounds the block-LOCAL residuals (rtol / sqrt(G)) over a pseudo-period
+        # (conv_detection_prime.c:11-249) and ignores a block that loses the threshold while it waits for the verdict
+        # (the pointer comparison at :84,:97,:173, replicated); the global residual lands within a multiple of rtol
+        # (measured, 2 B200: AM 26 x rtol, AMAM_GLOBAL 6 x, semi-local 6 x, local 2 x; the oracle's schedules: up to 17 x)
+        bound = rtol * 100.0
+        good = res["stop_reason"] == 0 and rel <= bound
+        ok &= good
+        print(f"{alg} {m}x{n}x{p} G={world} free-running: true rel residual {rel:.3e} (rtol {rtol:g}), outer its per block "
+              f"{[int(b) for b in its_all]}, {res['elapsed_s'] * 1e3:.1f} ms {'ok' if good else 'FAIL'}", flush=True)
+    eng.close()
+    D.barrier()
 if rank == 0:
     print("MGPU OK" if ok else "MGPU FAIL", flush=True)
 import torch.distributed as dist
