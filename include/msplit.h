@@ -213,7 +213,7 @@ int msp_op_mdot(msp_engine *e, int nv, const double *V /* nv x nb */, const doub
 int msp_op_maxpy(msp_engine *e, int nv, const double *V, const double *coef, double *w /* in/out */, double *norm);
 /* device micro-benchmark of the hot kernels on this engine's resident data: returns average ms per launch.
  * op: 0 spmv(ELL), 1 mdot(nv), 2 maxpy+norm(nv), 3 spmm(s), 4 copy (STREAM), 5 spmv with the input scaled on the fly,
- *     6 Gram contraction of nv columns */
+ *     6 Gram contraction of nv columns, 7 the same in panels of 8 columns (wide bases), 8 C := C T in panels (T = identity) */
 int msp_bench_kernel(msp_engine *e, int op, int nv, int iters, int flush_l2, double *ms_avg);
 
 /* standalone GMRES (gmres_solution.c:50-85): b = A 1, x0 = 0, one KSPSolve */

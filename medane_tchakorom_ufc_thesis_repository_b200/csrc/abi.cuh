@@ -360,6 +360,13 @@ int msp_bench_kernel(msp_engine *e, int op, int nv, int iters, int flush_l2, dou
   if ((op == 1 || op == 2) && (nv < 1 || nv > e->nvec)) MSP_FAIL("nv out of range");
   if (op == 3 && (nv < 1 || nv > e->smax)) MSP_FAIL("s out of range");
   if (op == 6 && (nv < 2 || nv > 9 || nv > e->smax + 1)) MSP_FAIL("gram: 2 <= columns <= min(9, s+1)");
+  if ((op == 7 || op == 8) && (nv < 2 || nv > e->smax + 1)) MSP_FAIL("wide gram / apply: 2 <= columns <= s+1");
+  if (op == 8) { // identity factor: the product leaves the columns unchanged
+    std::vector<double> T((size_t)nv * nv, 0.0);
+    for (int i = 0; i < nv; i++) T[(size_t)i * nv + i] = 1.0;
+    CK(cudaMemcpyAsync(e->dfac, T.data(), sizeof(double) * nv * nv, cudaMemcpyHostToDevice, e->st));
+    CK(cudaStreamSynchronize(e->st));
+  }
   double *flush = nullptr;
   const size_t flush_bytes = (size_t)256 << 20;
   if (flush_l2) CK(cudaMalloc(&flush, flush_bytes));
@@ -381,6 +388,8 @@ int msp_bench_kernel(msp_engine *e, int op, int nv, int iters, int flush_l2, dou
       case 4: k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, e->Wb[0], e->Wb[1]); break;
       case 5: { SpmvArgs a = spmv_args(e, e->Wb[0], e->Wb[1]); launch_spmv_w<0, false, true, false>(e, a, 0, nullptr); break; }
       case 6: launch_gram(e, nv, e->R, e->dfac); break;
+      case 7: launch_gram_wide(e, nv, e->R, e->dfac + (size_t)nv * nv); break;
+      case 8: launch_apply_upper(e, nv, e->R, e->dfac); break;
       default: MSP_FAIL("unknown op");
     }
     CK(cudaEventRecord(e1, e->st));

@@ -16,11 +16,12 @@ try:
     peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     pass
+s_basis = int(os.environ.get("KBENCH_S", "5"))
 if dim3:
-    e = S.Engine(N, N, N, s=5, max_restart=restart)
+    e = S.Engine(N, N, N, s=s_basis, max_restart=restart)
     W = 7
 else:
-    e = S.Engine(M, N, s=5, max_restart=restart)
+    e = S.Engine(M, N, s=s_basis, max_restart=restart)
     W = 5
 n = e.nb
 nnz = (5 * M * N - 2 * M - 2 * N) if not dim3 else (7 * N ** 3 - 6 * N * N)
@@ -50,6 +51,10 @@ for nv in (1, 4, 8, 16, 30):
     rec(f"maxpy+norm nv={nv}", e.bench_kernel(2, nv, iters=10), 8 * n * (nv + 2))
 rec("gram [R|b]^T[R|b] 6 columns", e.bench_kernel(6, 6, iters=10), 8 * n * 6)
 rec("spmm s=5", e.bench_kernel(3, 5, iters=10), 12 * nnz + 4 * n + 8 * n * 5 + 8 * n * 5)
+if e.s >= 20:
+    for nc in (11, 21):
+        rec(f"gram, panels of 8, {nc} columns", e.bench_kernel(7, nc, iters=10), 8 * n * nc)
+        rec(f"C := C T, panels of 8, {nc} columns", e.bench_kernel(8, nc, iters=10), 16 * n * nc)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump({"shape": shape, "dim": 3 if dim3 else 2, "spmv_format": fmt, "rows": rows},
           open(f"gpurun_out/kbench_{shape}{'_3d' if dim3 else ''}.json", "w"), indent=1)
