@@ -98,6 +98,14 @@ typedef struct {
    * running_bulk_test_local:3-7); 0 = none.  Synchronous variants agree on it collectively (one extra 1-double
    * allreduce per outer iteration, only when the cap is set), asynchronous blocks stop on their own clock. */
   double max_seconds;
+  /* asynchronous termination: 0 = conv_detection_prime.c (verification phases; what the compiled *_prime drivers use),
+   * 1 = the legacy counter-based detector of conv_detection.c (-min_convergence_count consecutive iterations under the
+   * threshold, SEND_CV / CANCEL_CV / GLOBAL_CV messages, exit after globalCV has held for max_traversal_ms;
+   * asynchronous-multisplitting.c.save:280-329) */
+  int detector;
+  int min_convergence_count;   /* MIN_CONVERGENCE_COUNT, config/default_run_variables: 4 (0 = 4) */
+  double max_traversal_ms;     /* MAX_TRAVERSAL_TIME; the reference measures a ping between the two block roots (13.21 ms on its
+                                  cluster); 0 = 0.5 ms, generous for NVLink peers */
 } msp_solve_opts;
 
 /* why the outer loop ended (msp_result.stop_reason) */

@@ -40,7 +40,7 @@ class SolveOpts(C.Structure):
         ("alg", C.c_int), ("s", C.c_int), ("rtol", C.c_double), ("inner", KspOpts), ("max_outer", C.c_int),
         ("record_history", C.c_int), ("profile", C.c_int), ("outer_type", C.c_int), ("outer_max_it", C.c_int),
         ("outer_rtol", C.c_double), ("outer_abstol", C.c_double), ("period", C.c_int * MAX_BLOCKS),
-        ("max_seconds", C.c_double),
+        ("max_seconds", C.c_double), ("detector", C.c_int), ("min_convergence_count", C.c_int), ("max_traversal_ms", C.c_double),
     ]
 
 

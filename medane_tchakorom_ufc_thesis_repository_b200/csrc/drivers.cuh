@@ -134,7 +134,7 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
   while (!done && !time_up && res->outer_its < max_outer) {
     if (alg == MSP_ALG_SM) {
       auto t0 = clk::now();
-      RC(op_inner_solve(e, &in, true, nullptr, nullptr, nullptr, !e->prof));
+      { StageRange stage("I_Solver"); RC(op_inner_solve(e, &in, true, nullptr, nullptr, nullptr, !e->prof)); }
       auto t1 = clk::now();
       res->stage_inner_s += secs(t0, t1);
       RC(exchange_sync(e));
@@ -155,13 +155,14 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
     for (int t = 0; t < s; t++) {
       RC(op_update_rhs(e));
       auto t0 = clk::now();
-      RC(op_inner_solve(e, &in, true, nullptr, nullptr, nullptr, !e->prof));
+      { StageRange stage("I_Solver"); RC(op_inner_solve(e, &in, true, nullptr, nullptr, nullptr, !e->prof)); }
       inner_this += secs(t0, clk::now());
       RC(exchange_sync(e));
       RC(op_push_iterate(e, t));
     }
     // R = A S (MatMatMult …-global.c:326); the LSQR path keeps the reference's raw basis [x^1 .. x^s], the exact solvers
     // use the basis of successive corrections
+    StageRange stage_outer("O_Solver");
     RC(op_spmm(e, alg, s, !lsqr));
     int lits = 0;
     double norm = 0.0, ln = 0.0;
@@ -211,6 +212,7 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
   e->prof_collect(res);
   e->prof = false;
   // closing exchange + true residual + error (comm_sync_send_and_receive_final comm.c:199, utils.c:575, :1045)
+  StageRange stage_last("Last");
   RC(op_publish_boundary(e));
   RC(exchange_sync(e));
   RC(op_resid_sumsq(e, true, 0));
@@ -326,7 +328,18 @@ struct AsyncRun {
   double thr_local = 0;
   double last_norm = 0;
   std::vector<double> uaug, alpha, all;
+  // legacy detector: time since globalCV became (and stayed) true (asynchronous-multisplitting.c.save:307-329)
+  bool lg_timer_on = false;
+  std::chrono::steady_clock::time_point lg_t0;
 };
+// after a step: has the run ended?  prime detector: state FINISHED; legacy: globalCV held for MAX_TRAVERSAL_TIME
+static bool async_finished(const msp_solve_opts *o, AsyncRun *run) {
+  if (o->detector != 1) return run->state == 3;
+  if (run->state != 1) { run->lg_timer_on = false; return false; }
+  if (!run->lg_timer_on) { run->lg_timer_on = true; run->lg_t0 = std::chrono::steady_clock::now(); return false; }
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - run->lg_t0).count();
+  return ms > (o->max_traversal_ms > 0.0 ? o->max_traversal_ms : 0.5);
+}
 
 static int slot_of_side(const msp_engine *e, int side) { return e->has_nb[0] ? side : 0; }
 
@@ -453,7 +466,10 @@ static int async_step(msp_engine *e, const msp_solve_opts *o, msp_result *res, A
     }
   }
   // root of the block: UnderThreshold + convergence detection state machine on the device
-  k_cd_step<<<1, 32, 0, e->st>>>(e->cd, 0, e->dsc + 1, run->thr_local);
+  if (o->detector == 1)
+    k_cd_legacy_step<<<1, 32, 0, e->st>>>(e->cd, e->dsc + 1, run->thr_local, o->min_convergence_count > 0 ? o->min_convergence_count : 4, run->iters);
+  else
+    k_cd_step<<<1, 32, 0, e->st>>>(e->cd, 0, e->dsc + 1, run->thr_local);
   e->launches++;
   CK(cudaMemcpyAsync(e->hsc + 48, e->cd, 8, cudaMemcpyDeviceToHost, e->st));
   RC(read_scalars(e, 1, 1));
@@ -488,16 +504,22 @@ static int engine_solve_async(msp_engine *e, const msp_solve_opts *o, msp_result
   RC(e->comm->barrier(e->st));
   const int max_outer = o->max_outer > 0 ? o->max_outer : 1000000;
   const int64_t l0 = e->launches;
+  e->prof = o->profile != 0; // per-class CUDA events around every hot launch, like the synchronous driver
+  struct ProfOff { msp_engine *e; ~ProfOff() { e->prof = false; } } prof_off{e};
   auto t0 = std::chrono::steady_clock::now();
-  bool time_up = false;
-  while (run.state != 3 && run.iters < max_outer && !time_up) {
+  bool time_up = false, fin = false;
+  while (!fin && run.iters < max_outer && !time_up) {
     RC(async_step(e, o, res, &run));
+    fin = async_finished(o, &run);
     if (o->max_seconds > 0.0) time_up = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= o->max_seconds;
   }
-  res->stop_reason = run.state == 3 ? MSP_STOP_CONVERGED : time_up ? MSP_STOP_MAX_SECONDS : MSP_STOP_MAX_OUTER;
+  if (o->detector == 1 && fin) { k_cd_legacy_send_global<<<1, 32, 0, e->st>>>(e->cd); e->launches++; } // comm_async_sendGlobalCV
+  res->stop_reason = fin ? MSP_STOP_CONVERGED : time_up ? MSP_STOP_MAX_SECONDS : MSP_STOP_MAX_OUTER;
   CK(cudaStreamSynchronize(e->st));
   res->elapsed_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   res->kernel_launches = e->launches - l0;
+  e->prof_collect(res);
+  e->prof = false;
   RC(e->comm->barrier(e->st));
   return async_finish(e, res, &run);
 }
@@ -536,10 +558,15 @@ static int engine_solve_async_group(msp_group *g, const msp_solve_opts *o, msp_r
   for (long long tick = 0; nfin < G && tick < max_ticks; tick++) {
     for (int k = 0; k < G; k++) {
       const int per = o->period[k] > 0 ? o->period[k] : 1;
-      if (tick % per || runs[k].state == 3) continue;
+      if (tick % per || runs[k].state == 3) continue; // (legacy detector: state 3 is set by the host once the hold has passed)
       cudaSetDevice(g->eng[k]->device);
       RC(async_step(g->eng[k], o, &res[k], &runs[k]));
       CK(cudaStreamSynchronize(g->eng[k]->st));
+      if (o->detector == 1) {
+        // deterministic schedule: the wall-clock hold becomes "globalCV seen at two consecutive steps of this block"
+        if (runs[k].state == 1 && runs[k].lg_timer_on) { runs[k].state = 3; k_cd_legacy_send_global<<<1, 32, 0, g->eng[k]->st>>>(g->eng[k]->cd); }
+        runs[k].lg_timer_on = (runs[k].state == 1);
+      }
       if (runs[k].state == 3) nfin++;
     }
   }

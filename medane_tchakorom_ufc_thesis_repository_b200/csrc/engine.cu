@@ -5,6 +5,7 @@
 
 #include <cub/device/device_scan.cuh>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h> // header-only NVTX v3: ranges named after the reference's PetscLogStages (no-ops without a profiler)
 
 #include <algorithm>
 #include <atomic>
@@ -40,6 +41,12 @@ static thread_local std::string g_err;
     int rc_ = (call);                                                                  \
     if (rc_) return rc_;                                                               \
   } while (0)
+
+// the reference's four log stages ("Loading", "I_Solver", "O_Solver", "Last"; …multisplitting.c:52-62, …-global.c:81-89) as NVTX ranges
+struct StageRange {
+  explicit StageRange(const char *name) { nvtxRangePushA(name); }
+  ~StageRange() { nvtxRangePop(); }
+};
 
 static int g_num_sms = 148;
 static inline int grid_for(long long work_items, int per_sm = 8) {
@@ -389,6 +396,7 @@ static int op_compute_rhs_ones(msp_engine *e) {
 
 static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   if (!p || !out) MSP_FAIL("null argument");
+  StageRange stage("Loading");
   if (p->dim != 2 && p->dim != 3) MSP_FAIL("dim must be 2 or 3");
   if (p->nblocks < 1 || p->nblocks > MSP_MAX_BLOCKS || p->block < 0 || p->block >= p->nblocks) MSP_FAIL("bad block / nblocks");
   if (p->max_restart < 1 || p->max_restart > MSP_MAX_RESTART) MSP_FAIL("max_restart out of range (1..64)");
@@ -405,6 +413,8 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   e->ntot = (long long)nx * ny * nz;
   if (layers % p->nblocks) { delete e; MSP_FAIL("grid lines (2-D) / planes (3-D) must be divisible by the number of blocks"); }
   if (e->ntot / p->nblocks > 2000000000LL) { delete e; MSP_FAIL("block too large for 32-bit indices"); }
+  // rowptr / nnz are int32 like PetscInt of the reference build (config/petsc/arch-linux-mpich-g5k-opt.py:46)
+  if ((e->ntot / p->nblocks) * (p->dim == 2 ? 5 : 7) > 2147483647LL) { delete e; MSP_FAIL("block has more than 2^31-1 non-zeros: use more blocks (32-bit indices, as in the reference's PETSc build)"); }
   e->nb = (int)(e->ntot / p->nblocks);
   e->off = (int)((long long)e->nb * p->block);
   e->ld = ((long long)e->nb + 63) / 64 * 64;
@@ -420,28 +430,34 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
       cudaMalloc(&e->eval, sizeof(double) * (size_t)e->ld * e->W) != cudaSuccess) { g_err = "out of device memory (ELL)"; return fail(1); }
   k_csr_to_ell<<<grid_for(e->ld, 16), MSPK_THREADS, 0, e->st>>>(e->nb, e->W, e->ld, e->off, e->rp, e->ci, e->va, e->ecol, e->eval);
   {
+    // every CUDA call of the setup is checked: a failure here (out of memory on a shared GPU, a sticky error of an earlier
+    // launch) must surface as an error of msp_create, not as a wrong matrix
+    auto ok_ = [&](cudaError_t er, const char *what) { if (er == cudaSuccess) return true; g_err = std::string(what) + ": " + cudaGetErrorString(er); return false; };
     int *flag = nullptr;
-    if (cudaMalloc(&flag, sizeof(int) * ((size_t)e->nb + 1)) != cudaSuccess) { g_err = "oom"; return fail(1); }
-    cudaMemsetAsync(flag, 0, sizeof(int) * ((size_t)e->nb + 1), e->st);
-    k_mark_boundary<<<grid_for(e->nb, 16), MSPK_THREADS, 0, e->st>>>(e->nb, e->W, e->ld, e->ecol, flag);
-    cudaStreamSynchronize(e->st);
+    if (!ok_(cudaMalloc(&flag, sizeof(int) * ((size_t)e->nb + 1)), "cudaMalloc(boundary flags)")) return fail(1);
+    bool good = ok_(cudaMemsetAsync(flag, 0, sizeof(int) * ((size_t)e->nb + 1), e->st), "cudaMemsetAsync(boundary flags)");
+    if (good) {
+      k_mark_boundary<<<grid_for(e->nb, 16), MSPK_THREADS, 0, e->st>>>(e->nb, e->W, e->ld, e->ecol, flag);
+      good = ok_(cudaGetLastError(), "k_mark_boundary launch") && ok_(cudaStreamSynchronize(e->st), "ELL conversion / boundary marking");
+    }
     // boundary rows live in the first and last H rows of a strip: fetch only those flags
     std::vector<int> hf;
     std::vector<int> rows;
     int span = std::min(e->nb, e->H);
     hf.resize(span);
-    cudaMemcpy(hf.data(), flag, sizeof(int) * span, cudaMemcpyDeviceToHost);
-    for (int i = 0; i < span; i++) if (hf[i]) rows.push_back(i);
-    if (e->nb > span) {
+    good = good && ok_(cudaMemcpy(hf.data(), flag, sizeof(int) * span, cudaMemcpyDeviceToHost), "cudaMemcpy(boundary flags)");
+    for (int i = 0; good && i < span; i++) if (hf[i]) rows.push_back(i);
+    if (good && e->nb > span) {
       int start = std::max(span, e->nb - span);
-      cudaMemcpy(hf.data(), flag + start, sizeof(int) * (e->nb - start), cudaMemcpyDeviceToHost);
-      for (int i = 0; i < e->nb - start; i++) if (hf[i]) rows.push_back(start + i);
+      good = ok_(cudaMemcpy(hf.data(), flag + start, sizeof(int) * (e->nb - start), cudaMemcpyDeviceToHost), "cudaMemcpy(boundary flags)");
+      for (int i = 0; good && i < e->nb - start; i++) if (hf[i]) rows.push_back(start + i);
     }
     cudaFree(flag);
+    if (!good) return fail(1);
     e->nbrow = (int)rows.size();
     if (e->nbrow) {
-      if (cudaMalloc(&e->brow, sizeof(int) * rows.size()) != cudaSuccess) { g_err = "oom"; return fail(1); }
-      cudaMemcpy(e->brow, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice);
+      if (!ok_(cudaMalloc(&e->brow, sizeof(int) * rows.size()), "cudaMalloc(boundary rows)")) return fail(1);
+      if (!ok_(cudaMemcpy(e->brow, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice), "cudaMemcpy(boundary rows)")) return fail(1);
     }
   }
   // ---- DIA view: which diagonals occur?  (decided from the assembled CSR; ELL stays the general fallback)
@@ -456,8 +472,9 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
     int hoor = 0;
     cudaMemcpyAsync(hb.data(), bitmap, sizeof(unsigned) * words, cudaMemcpyDeviceToHost, e->st);
     cudaMemcpyAsync(&hoor, oor, sizeof(int), cudaMemcpyDeviceToHost, e->st);
-    cudaStreamSynchronize(e->st);
+    const cudaError_t er_scan = cudaStreamSynchronize(e->st); // covers the two memsets, the launch and the copies
     cudaFree(bitmap); cudaFree(oor);
+    if (er_scan != cudaSuccess || cudaGetLastError() != cudaSuccess) { g_err = std::string("diagonal scan of the assembled strip failed: ") + cudaGetErrorString(er_scan); return fail(1); }
     std::vector<int> offs;
     for (size_t w = 0; w < words && offs.size() <= 8; w++)
       for (int b = 0; b < 32 && hb[w]; b++)

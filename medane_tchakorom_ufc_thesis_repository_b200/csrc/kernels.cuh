@@ -1400,6 +1400,9 @@ struct CdState {
   CdMailbox *inbox;     // own mailbox (written by peers)
   CdMailbox *outbox[2]; // neighbours' mailboxes (peer mapped); cell index = my slot in their table
   int my_slot_at[2];
+  // legacy counter-based detector (conv_detection.c): see k_cd_legacy_step
+  int lg_not_lcv, lg_count, lg_pre, lg_slcv, lg_global, lg_dest;
+  int lg_prev_s[2], lg_prev_c[2];
 };
 
 // seqlock cell: seq odd = being written.  Writer: seq = 2q+1, payload, seq = 2q+2.  Reader: consume when seq is even,
@@ -1536,6 +1539,58 @@ __global__ void k_cd_step(CdState *s, int under, const double *local_norm_sq, do
 }
 
 // ------------------------------------------------------------------------------------------------
+// Legacy counter-based termination (src/utils/conv_detection.c:6-173, driven as in
+// src/asynchronous-multisplitting/asynchronous-multisplitting.c.save:283-329).  A block is "pre-converged"
+// while its local residual is under the threshold; after MIN_CONVERGENCE_COUNT consecutive pre-converged iterations it is
+// "strictly locally converged" (sLocalCV).  It then reports to the one neighbour that has not reported yet (SEND_CV carrying
+// the iteration number), cancels that report if it loses the threshold (CANCEL_CV), and declares global convergence when
+// every neighbour has reported while it is itself converged.  The host holds the loop for MAX_TRAVERSAL_TIME after
+// globalCV and then tells the neighbours (GLOBAL_CV).  Mailbox cells: type 0 = SEND_CV, 1 = CANCEL_CV, 3 = GLOBAL_CV.
+// Generalisation of the 2-block code (dest_node = neighbors[0], conv_detection.c:63): the report goes to the first
+// neighbour whose newest message is not a report (prevIterNumS <= prevIterNumC).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_cd_legacy_step(CdState *s, const double *local_norm_sq, double thr, int threshold_slcv, int current_iteration) {
+  if (threadIdx.x || blockIdx.x) return;
+  const int NN = s->nb_neighbors;
+  s->lg_pre = (sqrt(*local_norm_sq) <= thr) ? 1 : 0;
+  // comm_async_convDetection conv_detection.c:6-81
+  if (!s->lg_slcv) {
+    if (s->lg_pre) { s->lg_count += 1; if (s->lg_count == threshold_slcv) s->lg_slcv = 1; }
+    else s->lg_count = 0;
+  } else if (!s->lg_pre) {
+    s->lg_slcv = 0; s->lg_count = 0;
+    if (s->lg_dest != -1) cd_send(s, s->lg_dest, 1, current_iteration, 0);
+  } else if (s->lg_not_lcv == 0) {
+    s->lg_global = 1;
+  } else if (s->lg_not_lcv == 1) {
+    int dest = 0;
+    for (int i = 0; i < NN; i++) if (s->lg_prev_s[i] <= s->lg_prev_c[i]) { dest = i; break; }
+    s->lg_dest = dest;
+    cd_send(s, dest, 0, current_iteration, 0);
+  }
+  int a, b;
+  for (int sl = 0; sl < NN; sl++) if (cd_recv(s, sl, 0, &a, &b)) {   // comm_async_recvSPartialCV :83-113
+    if (s->lg_prev_s[sl] < s->lg_prev_c[sl] && s->lg_prev_c[sl] < a) { s->lg_not_lcv -= 1; if (s->lg_not_lcv < 0) s->lg_not_lcv = 0; }
+    if (s->lg_prev_s[sl] < a) s->lg_prev_s[sl] = a;
+  }
+  for (int sl = 0; sl < NN; sl++) if (cd_recv(s, sl, 1, &a, &b)) {   // comm_async_recvCancelSPartialCV :115-146
+    if (s->lg_prev_c[sl] < s->lg_prev_s[sl] && s->lg_prev_s[sl] < a) {
+      s->lg_not_lcv += 1; if (s->lg_not_lcv > NN) s->lg_not_lcv = NN;
+      s->lg_global = 0;
+    }
+    if (s->lg_prev_c[sl] < a) s->lg_prev_c[sl] = a;
+  }
+  for (int sl = 0; sl < NN; sl++) if (cd_recv(s, sl, 3, &a, &b)) s->lg_global = a ? 1 : 0;   // comm_async_recvGlobalCV :148-160
+  s->state = s->lg_global ? 1 : 0; // what the host reads: 1 = globalCV (it then runs the MAX_TRAVERSAL_TIME hold)
+  s->state_seen = 0;
+}
+// comm_async_sendGlobalCV conv_detection.c:162-172, after the loop
+__global__ void k_cd_legacy_send_global(CdState *s) {
+  if (threadIdx.x || blockIdx.x) return;
+  for (int i = 0; i < s->nb_neighbors; i++) cd_send(s, i, 3, 1, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
 // asynchronous boundary exchange (comm_async_test_and_send_prime / comm_async_probe_and_receive_prime,
 // comm.c:455-554): the payload (one boundary layer) is stored into the neighbour's double-buffered receive
 // window, then a header {seq, PhaseTag, iteration} is released.  The receiver takes the newest header it
@@ -1591,4 +1646,7 @@ __global__ void k_cd_init(CdState *s, int me, int nblocks, CdMailbox *inbox, CdM
   for (int i = 0; i < 2; i++) { s->last_iter[i] = -1; s->responses[i] = 0; }
   cd_init_state(s);
   s->under = 0; s->phase_tag = 0; s->state_seen = 0; s->response_sent = 0;
+  // legacy detector (asynchronous-multisplitting.c.save:136-151): nbNeigNotLCV = nbNeighbors, prevIterNumS = -1, prevIterNumC = 0
+  s->lg_not_lcv = s->nb_neighbors; s->lg_count = 0; s->lg_pre = 0; s->lg_slcv = 0; s->lg_global = 0; s->lg_dest = -1;
+  for (int i = 0; i < 2; i++) { s->lg_prev_s[i] = -1; s->lg_prev_c[i] = 0; }
 }

@@ -9,9 +9,12 @@
  * like the PETSc options database does, and prints the log lines the reference's log scrapers rely on
  * (utils.c:668-729).  All numerics happen behind the C-ABI of libmsplit.so (include/msplit.h).
  *
- * Extensions: -minimizer tsqr|lsqr|gram (default tsqr = exact least squares; gram = normal equations on R'R;
- * lsqr = the reference's PETSc LSQR, driven by
- * -outer{K}_ksp_max_it / -outer{K}_ksp_rtol / -outer{K}_ksp_atol), -alg <iSolve name | reference binary name>, -p <depth> (3-D, poisson3DMatrix), -nblocks G
+ * Extensions: -minimizer tsqr|lsqr|gram|cg|cgne (default tsqr = exact least squares; gram = normal equations on R'R by
+ * Cholesky; cg = the same system by PETSc's CG, the reference's `outer_solver` with its default -outer_ksp_type cg;
+ * cgne = `outer_solver_cgne`; lsqr = the reference's PETSc LSQR; the iterative ones are driven by
+ * -outer{K}_ksp_max_it / -outer{K}_ksp_rtol / -outer{K}_ksp_atol), -detector prime|legacy (asynchronous termination:
+ * conv_detection_prime.c or the counter-based conv_detection.c with -min_convergence_count and -max_traversal_ms),
+ * -max_seconds T (wall-clock cap of the outer loop, the scripts' `timeout` wrapper), -alg <iSolve name | reference binary name>, -p <depth> (3-D, poisson3DMatrix), -nblocks G
  * (default: the reference's np/npb = 2; 1 for GMRES), -devices 0,1,... (one entry per block, default: block K on
  * GPU K mod #GPUs), -max_outer N, -period a,b,... (deterministic asynchronous schedule, tests only).
  */
@@ -22,6 +25,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 typedef struct { int argc; char **argv; } optdb;
 
@@ -152,7 +156,7 @@ int main(int argc, char **argv) {
   opt_int(&db, "-npb", &npb); opt_real(&db, "-rtol", &rtol); opt_real(&db, "-atol", &atol);
   opt_int(&db, "-min_convergence_count", &min_cc); opt_int(&db, "-max_outer", &max_outer);
   opt_int(&db, "-nblocks", &nblocks);
-  if (npb != 1) fprintf(stderr, "msolve: -npb %d ignored: a Jacobi block is one GPU here\n", npb);
+  if (npb != 1) fprintf(stderr, "msolve: -npb %d ignored: a Jacobi block is one GPU here (the reference's npb ranks of a block share one device)\n", npb);
   if (nblocks < 0) nblocks = (alg == MSP_ALG_GMRES) ? 1 : 2; /* iSolve:332-338: np/npb == 2 */
   if (nblocks > MSP_MAX_BLOCKS) { fprintf(stderr, "msolve: too many blocks\n"); return 2; }
   const int uses_s = !(alg == MSP_ALG_SM || alg == MSP_ALG_AM || alg == MSP_ALG_GMRES);
@@ -185,7 +189,9 @@ int main(int argc, char **argv) {
     if (mz && *mz) {
       if (!strcasecmp(mz, "lsqr")) outer_type = 1;
       else if (!strcasecmp(mz, "gram") || !strcasecmp(mz, "normal")) outer_type = 2;
-      else if (strcasecmp(mz, "tsqr") && strcasecmp(mz, "qr")) { fprintf(stderr, "msolve: -minimizer %s unknown (tsqr | lsqr | gram)\n", mz); return 2; }
+      else if (!strcasecmp(mz, "cg")) outer_type = 3;
+      else if (!strcasecmp(mz, "cgne")) outer_type = 4;
+      else if (strcasecmp(mz, "tsqr") && strcasecmp(mz, "qr")) { fprintf(stderr, "msolve: -minimizer %s unknown (tsqr | lsqr | gram | cg | cgne)\n", mz); return 2; }
     }
     const char *pre[] = {"outer_", "outer1_"};
     for (int i = 0; i < 2; i++) {
@@ -236,15 +242,32 @@ int main(int argc, char **argv) {
   }
 
   msp_group *g = NULL;
+  struct timespec ts0, ts1;
+  clock_gettime(CLOCK_MONOTONIC, &ts0);
   CHECK(msp_group_create(&prob, nblocks, devices, &g));
+  clock_gettime(CLOCK_MONOTONIC, &ts1);
+  const double stage_loading_s = (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec); /* "Loading" stage: assembly, split, vectors, b = A 1 */
   msp_solve_opts so;
   memset(&so, 0, sizeof so);
+  {
+    double max_seconds = 0.0, trav = 0.0;
+    const char *det = opt_find(&db, "-detector", NULL);
+    opt_real(&db, "-max_seconds", &max_seconds); opt_real(&db, "-max_traversal_ms", &trav);
+    so.max_seconds = max_seconds; so.max_traversal_ms = trav; so.min_convergence_count = min_cc;
+    if (det && *det) {
+      if (!strcasecmp(det, "legacy")) so.detector = 1;
+      else if (strcasecmp(det, "prime")) { fprintf(stderr, "msolve: -detector %s unknown (prime | legacy)\n", det); return 2; }
+    }
+  }
   so.alg = alg; so.s = uses_s ? s : 0; so.rtol = rtol; so.inner = inner; so.max_outer = max_outer; so.record_history = 1;
   so.outer_type = outer_type; so.outer_max_it = outer_max_it; so.outer_rtol = outer_rtol; so.outer_abstol = outer_atol;
   so.profile = opt_flag(&db, "-log_view"); /* per-event device times, like PETSc's -log_view (events bracket every launch) */
   for (int k = 0; k < nblocks; k++) so.period[k] = periods[k];
   msp_result *res = (msp_result *)calloc((size_t)nblocks, sizeof(msp_result));
+  clock_gettime(CLOCK_MONOTONIC, &ts0);
   CHECK(msp_group_solve(g, &so, res));
+  clock_gettime(CLOCK_MONOTONIC, &ts1);
+  const double solve_wall_s = (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec);
 
   printf("Global norm of b %e \n", res[0].norm0); /* …multisplitting.c:157 */
   if (opt_flag(&db, "-print_history"))
@@ -259,10 +282,15 @@ int main(int argc, char **argv) {
   printf("Final residual norm 2 = %e \n", res[0].final_residual); /* utils.c:699 */
   printf("Erreur : %e \n", res[0].error);                        /* …multisplitting.c:229 */
   if (opt_flag(&db, "-log_view")) {
-    /* the reference's PetscLogStage split (…-global.c:81-89), host seconds of block 0 */
+    /* the reference's four PetscLogStages (…multisplitting.c:52-62, …-global.c:81-89), host seconds of block 0 */
+    printf("Stage Loading (assembly, splitting, vectors, right-hand side): %f s\n", stage_loading_s);
     printf("Stage I_Solver (inner GMRES solves): %f s\n", res[0].stage_inner_s);
     printf("Stage O_Solver (exchange, A*S, minimisation, convergence test): %f s\n", res[0].stage_outer_s);
-    if (res[0].outer_solver_its) printf("Outer solver (LSQR) iterations: %lld\n", (long long)res[0].outer_solver_its);
+    {
+      double last = solve_wall_s - res[0].stage_inner_s - res[0].stage_outer_s; /* closing exchange, true residual, error */
+      printf("Stage Last (closing exchange, final residual, error): %f s\n", last > 0.0 ? last : 0.0);
+    }
+    if (res[0].outer_solver_its) printf("Outer solver (LSQR / CG / CGNE) iterations: %lld\n", (long long)res[0].outer_solver_its);
     /* self time per event in microseconds, in the layout of `-log_view ::ascii_flamegraph` (tmp/function-calling-stack:6-13) */
     printf("total solving;I_Solver stage;KSPSolve;KSPGMRESOrthog;VecMDot %.0f\n", res[0].t_mdot_ms * 1e3);
     printf("total solving;I_Solver stage;KSPSolve;KSPGMRESOrthog;VecMAXPY %.0f\n", res[0].t_maxpy_ms * 1e3);

@@ -312,7 +312,8 @@ def comm_unique_id() -> bytes:
 
 def make_solve_opts(alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_outer=0, record_history=True,
                     periods: Optional[Sequence[int]] = None, profile=False, outer_type="tsqr", outer_max_it=100,
-                    outer_rtol=1e-15, outer_abstol=1e-100, max_seconds=0.0) -> SolveOpts:
+                    outer_rtol=1e-15, outer_abstol=1e-100, max_seconds=0.0, detector="prime", min_convergence_count=4,
+                    max_traversal_ms=0.0) -> SolveOpts:
     o = SolveOpts()
     o.alg = ALG[alg] if isinstance(alg, str) else int(alg)
     o.s = s
@@ -324,6 +325,9 @@ def make_solve_opts(alg, s=0, rtol=1e-6, inner: Optional[KspOpts] = None, max_ou
     o.outer_type = {"tsqr": 0, "qr": 0, "lsqr": 1, "gram": 2, "normal": 2, "cg": 3, "cgne": 4}[outer_type]
     o.outer_max_it, o.outer_rtol, o.outer_abstol = outer_max_it, outer_rtol, outer_abstol
     o.max_seconds = float(max_seconds)
+    o.detector = {"prime": 0, "legacy": 1}[detector]
+    o.min_convergence_count = int(min_convergence_count)
+    o.max_traversal_ms = float(max_traversal_ms)
     for i in range(_lib.MAX_BLOCKS):
         o.period[i] = periods[i] if periods and i < len(periods) else 0
     return o

@@ -519,6 +519,32 @@ def test_async_free_running_reaches_residual(S, alg, s, G):
     grp.close()
 
 
+@pytest.mark.parametrize("alg,s,G,periods", [("AM", 0, 2, None), ("AM", 0, 3, [1, 2, 1]), ("AMAM_GLOBAL", 3, 2, None), ("AMAM_LOCAL", 3, 4, None)])
+def test_legacy_counter_detector(S, alg, s, G, periods):
+    """the legacy termination of conv_detection.c (MIN_CONVERGENCE_COUNT consecutive iterations under the
+    threshold, SEND_CV / CANCEL_CV / GLOBAL_CV messages, exit once globalCV has held), free-running and under a
+    deterministic schedule; generalised from the reference's 2 blocks to a chain.  Judged like every asynchronous run:
+    all blocks leave through the protocol and the true residual after the closing exchange is within a multiple of rtol."""
+    grp = S.Group(32, 36, nblocks=G, s=s, max_restart=30)
+    inner = S.ksp_opts(restart=30, max_it=3, rtol=1e-10, abstol=1e-100)
+    res = grp.solve(alg, s=s, rtol=1e-5, inner=inner, max_outer=20000, periods=periods, detector="legacy", min_convergence_count=4,
+                    max_traversal_ms=0.2)
+    assert all(r["stop_reason"] == 0 and 4 <= r["outer_its"] < 20000 for r in res), [(r["stop_reason"], r["outer_its"]) for r in res]
+    assert res[0]["final_residual"] <= 1e-3 * res[0]["norm0"]
+    # a block cannot have left before it saw MIN_CONVERGENCE_COUNT iterations under the threshold
+    thr = 1e-5 / np.sqrt(G) * res[0]["norm0"]
+    for r in res:
+        assert np.sum(r["hist"] <= thr) >= 4
+    # the same group runs the default (prime) detector afterwards: state is reset per solve
+    for e in grp.engines:
+        e.x = np.zeros(e.nb)
+        for side in (0, 1):
+            e.set_halo(side, np.zeros(e.H))
+    res2 = grp.solve(alg, s=s, rtol=1e-5, inner=inner, max_outer=20000, periods=periods)
+    assert all(r["stop_reason"] == 0 for r in res2)
+    grp.close()
+
+
 def test_time_to_rtol_1024_one_block(S):
     """The metric as BASELINE.json names it (SMSM time-to-rtol 1e-6), on a grid where it is reachable: 1024x1024, one
     block; outer-iteration count against the oracle run recorded in tests/golden/smsm_global_1024_to_rtol.json."""
@@ -777,7 +803,7 @@ def test_collective_surface_one_thread_per_block(S, oracle, kind, outer_type):
 
 
 @pytest.mark.parametrize("outer_type", ["cg", "cgne"])
-@pytest.mark.parametrize("alg,G", [("SMSM_GLOBAL", 2), ("SMSM_LOCAL", 2), ("SMSM_SEMI_LOCAL", 3)])
+@pytest.mark.parametrize("alg,G", [("SMSM_GLOBAL", 2), ("SMSM_LOCAL", 2), ("SMSM_SEMI_LOCAL", 4)])
 def test_cg_and_cgne_minimisers(S, oracle, alg, G, outer_type):
     """The rest of the reference's outer-solver menu: `outer_solver` = PETSc CG on the explicit normal
     equations R'R alpha = R'b (utils.c:972-996, the default -outer_ksp_type cg of config/default_run_variables) and
