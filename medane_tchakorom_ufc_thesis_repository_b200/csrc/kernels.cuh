@@ -119,6 +119,9 @@ __device__ inline void ctl_cycle_begin(GmresCtl *c, double res) {
   c->it = 0;
   c->hapend = 0;
   c->refine = 0;
+  // a cycle enqueued ahead of time (deferred status reads) after the solve has already ended: nothing to do.  KSPSolve_GMRES
+  // leaves its loop on any reason, and on itcount >= max_it; the host-driven path never gets here in that state.
+  if (!c->first_cycle && (c->reason != 0 || c->its >= c->max_it)) { c->active = 0; return; }
   c->tt = res;
   c->inv = (res > 0.0) ? 1.0 / res : 0.0;
   c->inv_arr[0] = c->inv;

@@ -34,11 +34,13 @@ static int read_scalars(msp_engine *e, int first, int n) {
 
 // inner_solver utils.c:950-970 -> KSPSolve_GMRES.  One host synchronisation per
 // restart cycle; inside a cycle every decision is taken on the device.
-// `defer`: when the solve is known to be ONE restart cycle (max_it <= restart) and the caller does not ask for
-// its / reason / rnorm, nothing is read back and the host does not wait: the cycle's kernels decide everything on the
-// device, its iteration count is added to ctl->its_total, and the caller's next stream synchronisation covers it.
+// `defer`: when the solve is at most four restart cycles (max_it <= 4 restart) and the caller does not ask for
+// its / reason / rnorm, nothing is read back and the host does not wait: every cycle the solve can need is enqueued,
+// the kernels decide everything on the device (a cycle that starts after the solve has ended — converged, broken down,
+// max_it reached — turns all its launches into no-ops), the iteration count is added to ctl->its_total, and the
+// caller's next stream synchronisation covers it.
 static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, int *its_out, int *reason_out, double *rnorm_out, bool defer = false) {
-  defer = defer && !its_out && !reason_out && !rnorm_out && o->max_it <= o->restart;
+  defer = defer && !its_out && !reason_out && !rnorm_out && o->max_it <= 4 * o->restart;
   if (o->restart < 1 || o->restart > e->prob.max_restart) MSP_FAIL("restart exceeds max_restart of the engine");
   const bool guess_zero = !o->guess_nonzero;
   double *bnorm_sq = nullptr;
@@ -137,7 +139,11 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
       RC(enqueue_cycle());
     }
     first = false;
-    if (defer) return 0;
+    if (defer) {
+      itcount += nsteps; // upper bound: the device stops earlier if it converges
+      if (itcount >= o->max_it) return 0;
+      continue;
+    }
     CK(cudaStreamSynchronize(e->st));
     memcpy(&hc, e->hsc + 32, 16);
     itcount += hc.it;

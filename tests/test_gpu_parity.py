@@ -525,7 +525,7 @@ def test_legacy_counter_detector(S, alg, s, G, periods):
     threshold, SEND_CV / CANCEL_CV / GLOBAL_CV messages, exit once globalCV has held), free-running and under a
     deterministic schedule; generalised from the reference's 2 blocks to a chain.  Judged like every asynchronous run:
     all blocks leave through the protocol and the true residual after the closing exchange is within a multiple of rtol."""
-    grp = S.Group(32, 36, nblocks=G, s=s, max_restart=30)
+    grp = S.Group(36, 32, nblocks=G, s=s, max_restart=30)
     inner = S.ksp_opts(restart=30, max_it=3, rtol=1e-10, abstol=1e-100)
     res = grp.solve(alg, s=s, rtol=1e-5, inner=inner, max_outer=20000, periods=periods, detector="legacy", min_convergence_count=4,
                     max_traversal_ms=0.2)
