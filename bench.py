@@ -363,21 +363,28 @@ def run_gpu(args):
                                 "note": "P2P stores are fused into the solution-update kernel; this is the NCCL 1-double barrier plus "
                                         "the copy of the received layers: latency-bound, not bandwidth-bound"}
 
-    # ---- end-to-end through the public C-ABI with HOST buffers: per step H2D of b and x, one outer iteration, D2H of x ----
+    # ---- end-to-end through the public C-ABI with HOST buffers: per step H2D of b and x from pinned memory, one outer
+    #      iteration, D2H of x into pinned memory.  The pipelined entry points enqueue the uploads on the engine's stream
+    #      and send the result back on a second stream from a snapshot of x, so the download of step k overlaps the upload
+    #      and the compute of step k + 1; every byte of every step is inside the timed region (the last download is waited
+    #      for before the clock stops) ----
     b_host = torch.empty(n_local, dtype=torch.float64).pin_memory().numpy()
     x_host = torch.empty(n_local, dtype=torch.float64).pin_memory().numpy()
+    out_host = [torch.empty(n_local, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
     b_host[:] = eng.b
     x_host[:] = eng.x
     e2e_steps = max(1, min(args.steps, 3))
     D.barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.b = b_host
-        eng.x = x_host
+    for i in range(e2e_steps):
+        eng.set_b_async(b_host)
+        eng.set_x_async(x_host)
         steps(1)
-        eng.get_x(x_host)
+        eng.get_x_async(out_host[i % 2])
+    eng.copies_wait()
     D.barrier()
     e2e = D.reduce_max((time.perf_counter() - t0) / e2e_steps)
+    assert float(out_host[(e2e_steps - 1) % 2][0]) == float(eng.x[0])
 
     rel = res["last_norm"] / res["norm0"]
     line = {
@@ -524,7 +531,8 @@ def _main():
     ap.add_argument("--ttr-grid", type=int, default=TTR["grid"])
     ap.add_argument("--ttr-s", type=int, default=TTR["s"])
     ap.add_argument("--ttr-max-seconds", type=float, default=150.0)
-    ap.add_argument("--s", dest="s_basis", type=int, default=S_BASIS, help="minimisation basis size for --to-rtol runs")
+    ap.add_argument("--basis-size", dest="s_basis", type=int, default=S_BASIS,
+                    help="minimisation basis size s for --to-rtol runs (not `--s`: torchrun's parser takes it for a prefix of its own options)")
     ap.add_argument("--to-rtol", type=int, default=0, help="run --alg to rtol 1e-6 on an N x N (x N with --grid-depth > 1) grid and report seconds")
     ap.add_argument("--max-outer", type=int, default=100000)
     ap.add_argument("--inner-max-it", type=int, default=INNER["max_it"])

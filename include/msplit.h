@@ -170,6 +170,13 @@ int msp_set_b(msp_engine *e, const double *b);
 int msp_get_b(msp_engine *e, double *b);
 int msp_set_x(msp_engine *e, const double *x);
 int msp_get_x(msp_engine *e, double *x);
+/* pipelined variants for callers that step the solver from PAGE-LOCKED host buffers: the uploads are only enqueued on the
+ * engine's stream, the download leaves on a second stream from a snapshot of x, so the result of step k travels while step
+ * k + 1 uploads and computes.  The host buffers must stay valid (and the output unread) until msp_copies_wait returns. */
+int msp_set_b_async(msp_engine *e, const double *b_pinned);
+int msp_set_x_async(msp_engine *e, const double *x_pinned);
+int msp_get_x_async(msp_engine *e, double *x_pinned);
+int msp_copies_wait(msp_engine *e);
 /* neighbour boundary values this block currently holds (side 0 = block K-1, 1 = block K+1) */
 int msp_set_halo(msp_engine *e, int side, const double *h);
 int msp_get_halo(msp_engine *e, int side, double *h);

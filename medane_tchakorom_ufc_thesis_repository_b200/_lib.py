@@ -83,7 +83,7 @@ EXPORTS = [
     "msp_group_solve", "msp_comm_unique_id", "msp_comm_init", "msp_comm_export", "msp_comm_connect", "msp_comm_connect_block", "msp_solve",
     "msp_conv_detect_step", "msp_get_solution", "msp_split_blocks", "msp_compute_rhs_ones", "msp_residual_norm",
     "msp_connect_local", "msp_exchange_sync", "msp_async_reset", "msp_exchange_async_publish", "msp_exchange_async_poll",
-    "msp_minimize",
+    "msp_minimize", "msp_set_b_async", "msp_set_x_async", "msp_get_x_async", "msp_copies_wait",
 ]
 
 _lib = None
@@ -150,6 +150,9 @@ def lib() -> C.CDLL:
     L.msp_comm_connect_block.argtypes = [vp, C.c_int, C.c_char_p]
     L.msp_solve.argtypes = [vp, C.POINTER(SolveOpts), C.POINTER(Result)]
     L.msp_conv_detect_step.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    for nm in ("msp_set_b_async", "msp_set_x_async", "msp_get_x_async"):
+        getattr(L, nm).argtypes = [vp, f64p]
+    L.msp_copies_wait.argtypes = [vp]
     L.msp_get_solution.argtypes = [vp, f64p]
     L.msp_split_blocks.argtypes = [vp, C.c_int, i32p, i32p, f64p]
     L.msp_compute_rhs_ones.argtypes = [vp]

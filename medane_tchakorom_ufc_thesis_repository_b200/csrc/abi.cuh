@@ -135,6 +135,44 @@ VEC_GETTER(msp_get_b, b, e->nb)
 VEC_SETTER(msp_set_x, x, e->nb)
 VEC_GETTER(msp_get_x, x, e->nb)
 VEC_GETTER(msp_get_rhs, rhs, e->nb)
+// ---- pipelined host <-> device transfers (page-locked host buffers; valid until msp_copies_wait) ----
+int msp_set_b_async(msp_engine *e, const double *b) {
+  if (!e || !b) MSP_FAIL("null argument");
+  cudaSetDevice(e->device);
+  CK(cudaMemcpyAsync(e->b, b, sizeof(double) * (size_t)e->nb, cudaMemcpyHostToDevice, e->st));
+  return 0;
+}
+int msp_set_x_async(msp_engine *e, const double *x) {
+  if (!e || !x) MSP_FAIL("null argument");
+  cudaSetDevice(e->device);
+  CK(cudaMemcpyAsync(e->x, x, sizeof(double) * (size_t)e->nb, cudaMemcpyHostToDevice, e->st));
+  return 0;
+}
+int msp_get_x_async(msp_engine *e, double *x) {
+  if (!e || !x) MSP_FAIL("null argument");
+  cudaSetDevice(e->device);
+  if (!e->st_copy) {
+    CK(cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming));
+    CK(cudaMalloc(&e->xstage, sizeof(double) * (size_t)e->ld));
+  }
+  // the previous download must have left the staging buffer before it is overwritten
+  CK(cudaEventRecord(e->ev_copy, e->st_copy));
+  CK(cudaStreamWaitEvent(e->st, e->ev_copy, 0));
+  CK(cudaMemcpyAsync(e->xstage, e->x, sizeof(double) * (size_t)e->nb, cudaMemcpyDeviceToDevice, e->st)); // snapshot: x may be overwritten next
+  CK(cudaEventRecord(e->ev_copy, e->st));
+  CK(cudaStreamWaitEvent(e->st_copy, e->ev_copy, 0));
+  CK(cudaMemcpyAsync(x, e->xstage, sizeof(double) * (size_t)e->nb, cudaMemcpyDeviceToHost, e->st_copy));
+  return 0;
+}
+int msp_copies_wait(msp_engine *e) {
+  if (!e) MSP_FAIL("null engine");
+  cudaSetDevice(e->device);
+  CK(cudaStreamSynchronize(e->st));
+  if (e->st_copy) CK(cudaStreamSynchronize(e->st_copy));
+  return 0;
+}
+
 int msp_set_halo(msp_engine *e, int side, const double *h) {
   if (!e || !h || side < 0 || side > 1) MSP_FAIL("bad argument");
   cudaSetDevice(e->device);

@@ -135,6 +135,9 @@ struct msp_engine {
   std::vector<int> fcache_seq;
   int par = 0;
   unsigned long long ex_seq = 0; // synchronous exchanges done (neighbour-flag protocol)
+  // host <-> device pipelining (msp_*_async): results leave on their own stream from a snapshot of x, so the copy of step
+  // k overlaps the upload and the compute of step k + 1
+  cudaStream_t st_copy = nullptr; cudaEvent_t ev_copy = nullptr; double *xstage = nullptr;
   Comm *comm = nullptr;
   bool own_comm = false;
   CdState *cd = nullptr;
@@ -368,6 +371,9 @@ static int engine_free(msp_engine *e) {
   void *ptrs[] = {e->rp, e->ci, e->va, e->ecol, e->eval, e->dval, e->dmask, e->brow, e->b, e->rhs, e->x, e->halo[0], e->halo[1], e->V, e->Wb[0],
                   e->Wb[1], e->S, e->Slo, e->Shi, e->R, e->ctl, e->ws.partial, e->ws.counter, e->dsc, e->dfac, e->gram_partial, e->win.base, e->cd, e->aint, e->dec};
   for (void *p : ptrs) if (p) cudaFree(p);
+  if (e->st_copy) { cudaStreamSynchronize(e->st_copy); cudaStreamDestroy(e->st_copy); }
+  if (e->ev_copy) cudaEventDestroy(e->ev_copy);
+  if (e->xstage) cudaFree(e->xstage);
   if (e->hsc) cudaFreeHost(e->hsc);
   if (e->own_comm && e->comm) delete e->comm;
   if (e->st) cudaStreamDestroy(e->st);

@@ -146,6 +146,19 @@ class Engine:
         check(_lib.lib().msp_get_x(self.h, out))
         return out
 
+    # pipelined transfers from / to page-locked host arrays (valid until copies_wait)
+    def set_b_async(self, v):
+        check(_lib.lib().msp_set_b_async(self.h, v))
+
+    def set_x_async(self, v):
+        check(_lib.lib().msp_set_x_async(self.h, v))
+
+    def get_x_async(self, out):
+        check(_lib.lib().msp_get_x_async(self.h, out))
+
+    def copies_wait(self):
+        check(_lib.lib().msp_copies_wait(self.h))
+
     @property
     def rhs(self):
         return self._getv(_lib.lib().msp_get_rhs, self.nb)

@@ -878,6 +878,38 @@ def test_group_abort_reports_the_failing_block(S):
     grp.close()
 
 
+def test_pipelined_host_transfers(S):
+    """msp_set_b_async / msp_set_x_async / msp_get_x_async / msp_copies_wait (the e2e path of bench.py): same numbers as
+    the blocking calls; the download is a snapshot, so the next upload cannot tear it."""
+    import torch
+    e = S.Engine(48, 40, s=3, max_restart=30)
+    n = e.nb
+    rng = np.random.default_rng(9)
+    b = torch.from_numpy(rng.standard_normal(n)).pin_memory().numpy()
+    x0 = torch.from_numpy(rng.standard_normal(n)).pin_memory().numpy()
+    x1 = torch.from_numpy(rng.standard_normal(n)).pin_memory().numpy()
+    out = [torch.empty(n, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+    e.set_b_async(b)
+    e.set_x_async(x0)
+    e.get_x_async(out[0])
+    e.set_x_async(x1)          # overwrites x on the device while the first download may still be in flight
+    e.get_x_async(out[1])
+    e.copies_wait()
+    assert np.array_equal(out[0], x0) and np.array_equal(out[1], x1)
+    assert np.array_equal(e.b, b) and np.array_equal(e.x, x1)
+    inner = S.ksp_opts(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)
+    e.set_x_async(x0)
+    r = e.solve("SMSM_GLOBAL", s=3, rtol=1e-300, inner=inner, max_outer=1)
+    e.get_x_async(out[0])
+    e.copies_wait()
+    e2 = S.Engine(48, 40, s=3, max_restart=30)
+    e2.b = b
+    e2.x = x0
+    r2 = e2.solve("SMSM_GLOBAL", s=3, rtol=1e-300, inner=inner, max_outer=1)
+    assert np.array_equal(out[0], e2.x) and r["last_norm"] == r2["last_norm"]
+    e.close(); e2.close()
+
+
 def test_wall_clock_cap(S):
     """msp_solve_opts.max_seconds: all blocks leave at the same outer iteration, stop_reason says why."""
     grp = S.Group(256, 256, nblocks=2, s=5, max_restart=30)

@@ -44,7 +44,10 @@ for alg, m, n, p, s, rtol, inner in cases:
 # asynchronous variants, free-running across processes (no barrier inside the loop; NVLink-mapped headers, mailboxes and
 # TSQR-factor slots): judged on the true residual after the closing synchronous exchange (…-global_prime.c:503-516)
 async_cases = [
-    ("AM", 64, 64, 1, 0, 1e-5, dict(restart=30, max_it=20, rtol=1e-10, abstol=1e-100)),
+    # AM tests the residual of the inner solve itself (MatResidual(A_KK, rhs_K, x_K), …multisplitting_prime.c:343): with an
+    # accurate inner solve every block is "under the threshold" at once and the protocol ends the run early (measured: 8 blocks,
+    # max_it 20: 47 iterations, true residual 1.9e-2) — the reference's scripts cap the inner solve at 2..5 iterations
+    ("AM", 64, 64, 1, 0, 1e-5, dict(restart=30, max_it=3, rtol=1e-10, abstol=1e-100)),
     ("AMAM_GLOBAL", 64, 64, 1, 5, 1e-6, dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)),
     ("AMAM_SEMI_LOCAL", 64, 64, 1, 4, 1e-4, dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)),
     ("AMAM_LOCAL", 64, 64, 1, 4, 1e-4, dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)),
