@@ -28,9 +28,13 @@ cases = [
     dict(alg="SMSM_LOCAL", m=32, n=32, nblocks=2, s=5, rtol=1e-6, inner=inner20),
     dict(alg="SMSM_GLOBAL", m=12, n=12, p=12, nblocks=2, s=5, rtol=1e-6, inner=inner20),
     dict(alg="SMSM_SEMI_LOCAL", m=16, n=16, p=16, nblocks=2, s=5, rtol=1e-6, inner=dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100)),
-    # the north_star regime (3-D 7-point, 8 strips, wide bases s = 10 / 20: profiles/r02_sweep_512cube.json) at oracle size
-    dict(alg="SMSM_GLOBAL", m=32, n=32, p=32, nblocks=8, s=10, rtol=1e-6, inner=inner20),
-    dict(alg="SMSM_GLOBAL", m=32, n=32, p=32, nblocks=8, s=20, rtol=1e-6, inner=inner20),
+    # the north_star regime (3-D 7-point strips, wide bases s = 10 / 20: profiles/r02_sweep_512cube.json) at oracle size.
+    # Inexact inner solves (max_it 5): iterates well separated, value-for-value parity.  Accurate inner solves on small
+    # blocks (max_it 20): 21 nearly dependent columns, three least-squares solvers give three "minimal" residuals after the
+    # FIRST outer iteration (32^3, 8 blocks: oracle Householder 3.67e-3, device CholeskyQR2 3.50e-3, numpy lstsq 3.36e-3);
+    # the 48^3 case is kept for the iteration count and a loose value check, the 32^3 one was dropped (4-plane blocks)
+    dict(alg="SMSM_GLOBAL", m=32, n=32, p=32, nblocks=8, s=10, rtol=1e-6, inner=inner5),
+    dict(alg="SMSM_GLOBAL", m=32, n=32, p=32, nblocks=8, s=20, rtol=1e-6, inner=inner5),
     dict(alg="SMSM_GLOBAL", m=48, n=48, p=48, nblocks=4, s=20, rtol=1e-6, inner=inner20),
 ]
 runs = []

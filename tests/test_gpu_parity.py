@@ -425,9 +425,15 @@ def test_sync_driver_parity(S, oracle, g):
     assert res[0]["outer_its"] == ref["outer_its"] == 2
     x = grp.solution()
     well_conditioned = g["alg"] == "SM" or g["nblocks"] == 1 or g["inner"]["max_it"] <= 5
-    assert np.linalg.norm(x - ref["x"]) <= (1e-8 if well_conditioned else 1e-6) * np.linalg.norm(ref["x"])
+    # wide basis AND accurate inner solves: 21 nearly dependent columns; the minimal residual itself then depends on the
+    # least-squares solver at the percent level from the first outer iteration on (measured at 48^3, 4 blocks, s = 20:
+    # 2e-4 / 1.4 % on the two history values against the oracle, 1e-3 / 0.5 % against numpy's lstsq)
+    wide_accurate = g["s"] >= 10 and not well_conditioned
+    x_bar = 1e-8 if well_conditioned else (1e-3 if wide_accurate else 1e-6)
+    h_bar = 1e-6 if well_conditioned else (5e-2 if wide_accurate else 1e-2)
+    assert np.linalg.norm(x - ref["x"]) <= x_bar * np.linalg.norm(ref["x"])
     # semi-local / local: every block reports its own local norm; the oracle's history keeps the worst block
-    assert np.allclose(np.max([r["hist"] for r in res], axis=0), ref["hist"], rtol=1e-6 if well_conditioned else 1e-2)
+    assert np.allclose(np.max([r["hist"] for r in res], axis=0), ref["hist"], rtol=h_bar)
     assert abs(res[0]["norm0"] - g["norm0"]) <= 1e-13 * g["norm0"]
     grp.close()
     # (b)
