@@ -73,6 +73,11 @@ typedef struct {
   int s;       /* -s : minimisation basis size (0 if unused) */
   int max_restart; /* storage for the Krylov basis; >= every restart used later */
   int keep_csr;    /* keep the strip CSR on the device after setup (needed by msp_get_csr) */
+  /* -npb: GPUs per Jacobi block (the reference's ranks per block, computeDimensionRelatedVariables utils.c:652-666).
+   * 0 or 1: one GPU per block.  P > 1: `nblocks` counts the GPUs (strips), Jacobi blocks = nblocks / P, GPU r belongs to block
+   * r / P; the block's inner GMRES is then distributed over its P GPUs (boundary layers of every Krylov vector between the
+   * GPUs of a block, MDot and norm results summed over them).  Supported by SM, SMSM_GLOBAL and the stand-alone GMRES. */
+  int npb;
 } msp_problem;
 
 typedef struct {

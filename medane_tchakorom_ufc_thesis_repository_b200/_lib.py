@@ -31,7 +31,7 @@ class KspOpts(C.Structure):
 class Problem(C.Structure):
     _fields_ = [
         ("dim", C.c_int), ("m", C.c_int), ("n", C.c_int), ("p", C.c_int), ("block", C.c_int),
-        ("nblocks", C.c_int), ("s", C.c_int), ("max_restart", C.c_int), ("keep_csr", C.c_int),
+        ("nblocks", C.c_int), ("s", C.c_int), ("max_restart", C.c_int), ("keep_csr", C.c_int), ("npb", C.c_int),
     ]
 
 

@@ -452,25 +452,29 @@ int msp_gmres_solve(msp_engine *e, const msp_ksp_opts *o, msp_result *res) {
 // ---- group ----
 int msp_group_create(const msp_problem *prob, int nblocks, const int *devices, msp_group **out) {
   if (!prob || !out || nblocks < 1 || nblocks > MSP_MAX_BLOCKS) MSP_FAIL("bad argument");
+  const int npb = prob->npb > 1 ? prob->npb : 1;
+  if (nblocks % npb) MSP_FAIL("the number of engines must be a multiple of npb");
   msp_group *g = new msp_group();
   g->G = nblocks;
   g->sh = new LocalShared(nblocks);
+  if (npb > 1) for (int K = 0; K < nblocks / npb; K++) g->bsh.push_back(new LocalShared(npb));
   for (int k = 0; k < nblocks; k++) {
     msp_problem p = *prob;
     p.block = k; p.nblocks = nblocks;
     msp_engine *e = nullptr;
     int rc = engine_create(&p, devices ? devices[k] : 0, &e);
-    if (rc) { for (auto *x : g->eng) engine_free(x); delete g->sh; delete g; return rc; }
+    if (rc) { for (auto *x : g->eng) engine_free(x); for (auto *b : g->bsh) delete b; delete g->sh; delete g; return rc; }
     g->eng.push_back(e);
   }
   int rc = group_wire(g);
-  if (rc) { for (auto *x : g->eng) engine_free(x); delete g->sh; delete g; return rc; }
+  if (rc) { for (auto *x : g->eng) engine_free(x); for (auto *b : g->bsh) delete b; delete g->sh; delete g; return rc; }
   *out = g;
   return 0;
 }
 int msp_group_destroy(msp_group *g) {
   if (!g) return 0;
   for (auto *e : g->eng) engine_free(e);
+  for (auto *b : g->bsh) delete b;
   delete g->sh;
   delete g;
   return 0;
@@ -480,17 +484,17 @@ msp_engine *msp_group_engine(msp_group *g, int k) { return (g && k >= 0 && k < g
 
 int msp_group_solve(msp_group *g, const msp_solve_opts *o, msp_result *res) {
   if (!g || !o || !res) MSP_FAIL("null argument");
-  if (o->alg == MSP_ALG_GMRES) MSP_FAIL("use msp_gmres_solve for the stand-alone GMRES");
   if (o->alg >= MSP_ALG_AM) return engine_solve_async_group(g, o, res);
   std::vector<int> rcs(g->G, 0);
   std::vector<std::string> errs(g->G);
   std::vector<std::thread> th;
   g->sh->reset();
+  for (auto *b : g->bsh) b->reset();
   for (int k = 0; k < g->G; k++)
     th.emplace_back([&, k] {
       cudaSetDevice(g->eng[k]->device);
-      rcs[k] = engine_solve_sync(g->eng[k], o, &res[k]);
-      if (rcs[k]) { errs[k] = g_err; g->sh->abort(); } // wake the blocks waiting for this one in a collective
+      rcs[k] = (o->alg == MSP_ALG_GMRES) ? engine_gmres(g->eng[k], &o->inner, &res[k]) : engine_solve_sync(g->eng[k], o, &res[k]);
+      if (rcs[k]) { errs[k] = g_err; g->sh->abort(); for (auto *b : g->bsh) b->abort(); } // wake the blocks waiting for this one in a collective
     });
   for (auto &t : th) t.join();
   return group_first_error(rcs, errs);
@@ -517,8 +521,19 @@ int msp_comm_init(msp_engine *e, const void *id128, int rank, int nranks) {
   memcpy(&id, id128, 128);
   int rc = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
   if (rc) { delete c; MSP_FAIL(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?")); }
+  if (e->own_bcomm && e->bcomm) delete e->bcomm;
   if (e->own_comm && e->comm) delete e->comm;
   e->comm = c; e->own_comm = true;
+  e->bcomm = c; e->own_bcomm = false;
+  if (e->npb > 1) {
+    // the communicator of my Jacobi block (the reference's comm_jacobi_block, PetscSubcomm CONTIGUOUS …multisplitting.c:66-73)
+    if (!g_nccl.CommSplit) MSP_FAIL("ncclCommSplit not available in this NCCL (needed for npb > 1)");
+    NcclComm *b = new NcclComm();
+    b->rank = rank % e->npb; b->nranks = e->npb;
+    rc = g_nccl.CommSplit(c->comm, rank / e->npb, rank % e->npb, &b->comm, nullptr);
+    if (rc) { delete b; MSP_FAIL(std::string("ncclCommSplit: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?")); }
+    e->bcomm = b; e->own_bcomm = true;
+  }
   return 0;
 }
 int msp_comm_export(msp_engine *e, void *handle64) {

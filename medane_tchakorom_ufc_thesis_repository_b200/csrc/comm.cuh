@@ -86,6 +86,7 @@ struct NcclApi {
   int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, void *) = nullptr; // NCCL >= 2.18: the communicator of one Jacobi block
   const char *(*GetErrorString)(int) = nullptr;
   bool load() {
     if (h) return true;
@@ -97,6 +98,7 @@ struct NcclApi {
     CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
     AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
     GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    CommSplit = (int (*)(ncclComm_t, int, int, ncclComm_t *, void *))dlsym(h, "ncclCommSplit");
     return GetUniqueId && CommInitRank && CommDestroy && AllReduce;
   }
 };

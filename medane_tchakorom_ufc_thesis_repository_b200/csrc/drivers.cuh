@@ -102,6 +102,8 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
   msp_ksp_opts in = o->inner;
   in.initial_rtol = 1; in.guess_nonzero = 1; // inner_solver utils.c:956-957
   if (alg != MSP_ALG_SM && (s < 1 || s > e->smax)) MSP_FAIL("s exceeds the engine's basis storage");
+  if (e->npb > 1 && alg != MSP_ALG_SM && alg != MSP_ALG_SMSM_GLOBAL)
+    MSP_FAIL("a Jacobi block spread over several GPUs (npb > 1) is supported by SM, SMSM_GLOBAL and the stand-alone GMRES");
   const int max_outer = o->max_outer > 0 ? o->max_outer : 1000000;
   memset(res, 0, sizeof(*res));
   // global_norm_0 = computeFinalResidualNorm(x = 0) before the loop (…multisplitting.c:162) = ||b||; computed from b so
@@ -227,19 +229,21 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
 // gmres_solution.c:50-85
 static int engine_gmres(msp_engine *e, const msp_ksp_opts *o, msp_result *res) {
   memset(res, 0, sizeof(*res));
-  if (e->prob.nblocks != 1) MSP_FAIL("stand-alone GMRES runs on a single block");
+  if (e->prob.nblocks != e->npb) MSP_FAIL("stand-alone GMRES runs on a single block (one GPU, or npb = the number of GPUs)");
   CK(cudaMemsetAsync(e->x, 0, sizeof(double) * e->ld, e->st));
   CK(cudaMemcpyAsync(e->rhs, e->b, sizeof(double) * e->ld, cudaMemcpyDeviceToDevice, e->st));
   k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->b, 0.0, e->ws, 2, e->dsc + 0);
-  RC(read_scalars(e, 0, 1));
+  RC(allreduce_host(e, 0, 1));
   res->norm0 = std::sqrt(e->hsc[0]);
   msp_ksp_opts in = *o;
   in.guess_nonzero = 0;
+  RC(e->comm->barrier(e->st));
   EventPair ev;
   CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
   CK(cudaEventRecord(ev.a, e->st));
   const int64_t l0 = e->launches;
   RC(op_inner_solve(e, &in, false, &res->gmres_its, &res->gmres_reason, &res->gmres_rnorm));
+  RC(e->comm->barrier(e->st));
   CK(cudaEventRecord(ev.b, e->st));
   CK(cudaEventSynchronize(ev.b));
   float ms = 0.f;
@@ -248,9 +252,12 @@ static int engine_gmres(msp_engine *e, const msp_ksp_opts *o, msp_result *res) {
   res->kernel_launches = e->launches - l0;
   res->outer_its = res->gmres_its;
   res->last_norm = res->gmres_rnorm;
+  // true residual and error over all strips of the block (closing exchange of the boundary layers when there are several)
+  RC(op_publish_boundary(e));
+  RC(exchange_sync(e));
   RC(op_resid_sumsq(e, true, 0));
   k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->x, 1.0, e->ws, 2, e->dsc + 1);
-  RC(read_scalars(e, 0, 2));
+  RC(allreduce_host(e, 0, 2));
   res->final_residual = std::sqrt(e->hsc[0]);
   res->error = std::sqrt(e->hsc[1]);
   return 0;
@@ -260,9 +267,10 @@ static int engine_gmres(msp_engine *e, const msp_ksp_opts *o, msp_result *res) {
 // group: all blocks in one process
 // ------------------------------------------------------------------------------------------------
 struct msp_group {
-  int G = 0;
+  int G = 0; // engines (= strips = GPUs); Jacobi blocks = G / npb
   std::vector<msp_engine *> eng;
   LocalShared *sh = nullptr;
+  std::vector<LocalShared *> bsh; // one per Jacobi block when a block spans several engines (npb > 1)
 };
 
 // the error a group call reports: the first block failure that is not just the echo of another block's abort
@@ -281,8 +289,11 @@ static int group_first_error(const std::vector<int> &rcs, const std::vector<std:
 static int group_wire(msp_group *g) {
   for (int k = 0; k < g->G; k++) {
     msp_engine *e = g->eng[k];
+    if (e->own_bcomm && e->bcomm) delete e->bcomm;
     if (e->own_comm && e->comm) delete e->comm;
     e->comm = new LocalComm(g->sh, k); e->own_comm = true;
+    if (e->npb > 1) { e->bcomm = new LocalComm(g->bsh[k / e->npb], k % e->npb); e->own_bcomm = true; }
+    else { e->bcomm = e->comm; e->own_bcomm = false; }
     e->grp = g;
     for (int side = 0; side < 2; side++) {
       int nbk = side == 0 ? k - 1 : k + 1;
@@ -371,6 +382,7 @@ static int async_begin(msp_engine *e, const msp_solve_opts *o, msp_result *res, 
   const int G = e->prob.nblocks, s = o->s;
   memset(res, 0, sizeof(*res));
   if (o->outer_type != 0) MSP_FAIL("the LSQR and normal-equations minimisers are available for the synchronous variants only");
+  if (e->npb > 1) MSP_FAIL("the asynchronous variants run one GPU per Jacobi block (npb = 1)");
   if (o->alg != MSP_ALG_AM && (s < 1 || s > e->smax)) MSP_FAIL("s exceeds the engine's basis storage");
   for (int side = 0; side < 2; side++)
     if (e->has_nb[side] && !e->peer[side].base) MSP_FAIL("neighbour window not connected");

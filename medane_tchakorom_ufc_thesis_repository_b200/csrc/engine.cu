@@ -90,9 +90,12 @@ struct Window {
   CdMailbox *mailbox() const { return reinterpret_cast<CdMailbox *>(base + (size_t)4 * H + 8); }
   double *factor(int J) const { return base + (size_t)4 * H + 8 + 16 + (size_t)J * fslot; }
   // [0]: exchange sequence number published by the lower neighbour, [1]: by the upper neighbour (the 8 spare doubles at the end)
+  // [2], [3]: the same for the exchange of Krylov-vector layers inside a multi-GPU Jacobi block
   unsigned long long *flags() const { return reinterpret_cast<unsigned long long *>(base + (size_t)4 * H + 8 + 16 + (size_t)G * fslot); }
+  // boundary layers of the vector the block's distributed inner solve is about to multiply (npb > 1): [lo par0|lo par1|hi par0|hi par1]
+  double *vhalo(int side, int par) const { return base + (size_t)4 * H + 8 + 16 + (size_t)G * fslot + 8 + (size_t)(side * 2 + par) * H; }
   static int fslot_for(int smax) { return (smax + 1) * (smax + 1) + 2; }
-  static size_t size_for(int H, int G, int smax) { return sizeof(double) * ((size_t)4 * H + 8 + 16 + (size_t)G * fslot_for(smax) + 8); }
+  static size_t size_for(int H, int G, int smax) { return sizeof(double) * ((size_t)4 * H + 8 + 16 + (size_t)G * fslot_for(smax) + 8 + (size_t)4 * H); }
 };
 static_assert(sizeof(CdMailbox) == 128, "mailbox layout");
 
@@ -135,6 +138,12 @@ struct msp_engine {
   std::vector<int> fcache_seq;
   int par = 0;
   unsigned long long ex_seq = 0; // synchronous exchanges done (neighbour-flag protocol)
+  // a Jacobi block spread over npb GPUs: which neighbour strips belong to my block, the block's communicator, the exchange of
+  // Krylov-vector layers between the GPUs of the block
+  int npb = 1;
+  bool intra[2] = {false, false};
+  Comm *bcomm = nullptr; bool own_bcomm = false;
+  unsigned long long vex_seq = 0; int vpar = 0;
   // host <-> device pipelining (msp_*_async): results leave on their own stream from a snapshot of x, so the copy of step
   // k overlaps the upload and the compute of step k + 1
   cudaStream_t st_copy = nullptr; cudaEvent_t ev_copy = nullptr; double *xstage = nullptr;
@@ -375,6 +384,7 @@ static int engine_free(msp_engine *e) {
   if (e->ev_copy) cudaEventDestroy(e->ev_copy);
   if (e->xstage) cudaFree(e->xstage);
   if (e->hsc) cudaFreeHost(e->hsc);
+  if (e->own_bcomm && e->bcomm) delete e->bcomm;
   if (e->own_comm && e->comm) delete e->comm;
   if (e->st) cudaStreamDestroy(e->st);
   delete e;
@@ -407,6 +417,8 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   if (p->nblocks < 1 || p->nblocks > MSP_MAX_BLOCKS || p->block < 0 || p->block >= p->nblocks) MSP_FAIL("bad block / nblocks");
   if (p->max_restart < 1 || p->max_restart > MSP_MAX_RESTART) MSP_FAIL("max_restart out of range (1..64)");
   if (p->s < 0 || p->s > MSP_MAX_S) MSP_FAIL("s out of range (0..32)");
+  const int npb = p->npb > 1 ? p->npb : 1;
+  if (p->nblocks % npb) MSP_FAIL("the number of GPUs (nblocks) must be a multiple of npb (GPUs per Jacobi block)");
   RC(set_device(device));
   msp_engine *e = new msp_engine();
   e->device = device; e->prob = *p;
@@ -425,6 +437,9 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   e->off = (int)((long long)e->nb * p->block);
   e->ld = ((long long)e->nb + 63) / 64 * 64;
   e->has_nb[0] = p->block > 0; e->has_nb[1] = p->block < p->nblocks - 1;
+  e->npb = npb;
+  e->intra[0] = e->has_nb[0] && (p->block - 1) / npb == p->block / npb;
+  e->intra[1] = e->has_nb[1] && (p->block + 1) / npb == p->block / npb;
   if (cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess) { delete e; MSP_FAIL("stream create failed"); }
   int rc = 0;
   auto fail = [&](int r) { engine_free(e); return r; };
@@ -564,6 +579,7 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   if (ok && cudaMallocHost(&e->hsc, sizeof(double) * 256) != cudaSuccess) ok = false;
   if (!ok) { g_err = "out of device memory (vectors)"; return fail(1); }
   e->comm = new SelfComm(); e->own_comm = true;
+  e->bcomm = e->comm; e->own_bcomm = false; // one GPU per block until a group / msp_comm_init wires the block's ranks
   e->use_graphs = getenv("MSPLIT_NO_GRAPHS") == nullptr;
   if (op_compute_rhs_ones(e)) return fail(1);
   if (cudaStreamSynchronize(e->st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { g_err = "setup kernels failed"; return fail(1); }

@@ -183,6 +183,26 @@ __device__ inline void ctl_step_end(GmresCtl *c, double tt) {
   c->active = (c->reason == 0 && c->it < c->restart && c->its < c->max_it) ? 1 : 0;
 }
 
+// end of one classical Gram-Schmidt pass of step `it` (borthog2.c): hh[j] -= lhh[j] (lhh holds -<w, v_j>), decide on the
+// second pass (REFINE_IFNEEDED / REFINE_ALWAYS), otherwise close the step with tt = ||w||
+__device__ inline void ctl_cgs_pass_end(GmresCtl *c, double tt, int pass) {
+  const int it = c->it;
+  double *hh = &c->hh[(size_t)it * (MSPK_MAXK + 2)];
+  double hn = 0.0;
+  for (int j = 0; j <= it; j++) {
+    if (pass == 0) hh[j] = 0.0;
+    hh[j] -= c->lhh[j];
+    hn = fma(c->lhh[j], c->lhh[j], hn);
+  }
+  bool more = false;
+  if (pass == 0) {
+    if (c->cgs_refine == 2) more = true;
+    else if (c->cgs_refine == 1) more = (tt < sqrt(hn));
+  }
+  c->refine = more ? 1 : 0;
+  if (!more) ctl_step_end(c, tt);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K12  CSR assembly of the Poisson strips (poisson2DMatrix utils.c:247-293, poisson3DMatrix :30-121)
 // ------------------------------------------------------------------------------------------------
@@ -839,6 +859,7 @@ __global__ void __launch_bounds__(MSPK_THREADS, NVMAX > 16 ? 1 : 2) k_mdot(MdotA
 // Last block finishes the norm and runs the Hessenberg/Givens update + convergence test on the
 // device (K6), so no host round trip is needed inside a restart cycle.
 //   FIN 0: only store the norm       FIN 1: CGS pass epilogue (ctl_step_end / refinement decision)
+//   FIN 2: store the SUM OF SQUARES (a Jacobi block spread over several GPUs sums it over its ranks, then k_step_end)
 // ------------------------------------------------------------------------------------------------
 struct MaxpyArgs {
   int nb, nv;
@@ -939,26 +960,8 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
     if (threadIdx.x == 0) {
       ws.counter[ws_slot] = 0;
       const double tt = sqrt(tot);
-      if (a.norm_out) *a.norm_out = tt;
-      if (FIN == 1) {
-        GmresCtl *c = a.ctl;
-        const int it = c->it;
-        double *hh = &c->hh[(size_t)it * (MSPK_MAXK + 2)];
-        // borthog2.c: hh[j] -= lhh[j]  (lhh holds -<w,v_j>)
-        double hn = 0.0;
-        for (int j = 0; j <= it; j++) {
-          if (a.pass == 0) hh[j] = 0.0;
-          hh[j] -= c->lhh[j];
-          hn = fma(c->lhh[j], c->lhh[j], hn);
-        }
-        bool more = false;
-        if (a.pass == 0) {
-          if (c->cgs_refine == 2) more = true;
-          else if (c->cgs_refine == 1) more = (tt < sqrt(hn));
-        }
-        c->refine = more ? 1 : 0;
-        if (!more) ctl_step_end(c, tt);
-      }
+      if (a.norm_out) *a.norm_out = (FIN == 2) ? tot : tt; // FIN 2: the sum of squares, to be summed over the ranks of a block
+      if (FIN == 1) ctl_cgs_pass_end(a.ctl, tt, a.pass);
     }
   }
 }
@@ -1035,6 +1038,26 @@ __global__ void k_signal_neighbours(unsigned long long *flag_lo, unsigned long l
   if (flag_lo) *reinterpret_cast<volatile unsigned long long *>(flag_lo) = seq;
   if (flag_hi) *reinterpret_cast<volatile unsigned long long *>(flag_hi) = seq;
   __threadfence_system();
+}
+
+// ---- a Jacobi block spread over several GPUs (the reference's npb > 1): the pieces around the block-wide reductions ----
+// after the sum of squares of w has been summed over the ranks of the block: close the Gram-Schmidt pass of step guard_it
+__global__ void k_step_end(GmresCtl *c, const double *sumsq, int pass, int guard_it, int guard_refine) {
+  if (threadIdx.x || blockIdx.x) return;
+  if (!c->active || c->it != guard_it) return;
+  if (guard_refine && !c->refine) return;
+  ctl_cgs_pass_end(c, sqrt(*sumsq), pass);
+}
+// first / last boundary layer of a vector into the intra-block neighbours' windows, scaled by *scale (the Krylov basis is
+// stored un-normalised; the neighbour's SpMV does not scale what it reads from its halo).  guard_it as in the SpMV.
+__global__ void k_publish_boundary_scaled(int nb, int H, const double *__restrict__ v, const double *scale, const GmresCtl *ctl, int guard_it,
+                                          double *peer_lo, double *peer_hi) {
+  if (guard_it >= 0 && (!ctl->active || ctl->it != guard_it)) return;
+  const double sc = scale ? *scale : 1.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H; i += gridDim.x * blockDim.x) {
+    if (peer_lo) peer_lo[i] = v[i] * sc;
+    if (peer_hi) peer_hi[i] = v[nb - H + i] * sc;
+  }
 }
 
 // publish only the boundary layers (used after the minimisation rewrote x, and by the closing exchange)

@@ -156,8 +156,16 @@ int main(int argc, char **argv) {
   opt_int(&db, "-npb", &npb); opt_real(&db, "-rtol", &rtol); opt_real(&db, "-atol", &atol);
   opt_int(&db, "-min_convergence_count", &min_cc); opt_int(&db, "-max_outer", &max_outer);
   opt_int(&db, "-nblocks", &nblocks);
-  if (npb != 1) fprintf(stderr, "msolve: -npb %d ignored: a Jacobi block is one GPU here (the reference's npb ranks of a block share one device)\n", npb);
+  if (npb < 1) npb = 1;
   if (nblocks < 0) nblocks = (alg == MSP_ALG_GMRES) ? 1 : 2; /* iSolve:332-338: np/npb == 2 */
+  /* -npb P: P GPUs (strips) per Jacobi block, i.e. nblocks * P engines; the inner GMRES of a block is then distributed over them
+   * (SM, SMSM_GLOBAL, GMRES).  The other algorithms keep one strip per block and say so. */
+  if (npb > 1 && !(alg == MSP_ALG_SM || alg == MSP_ALG_SMSM_GLOBAL || alg == MSP_ALG_GMRES)) {
+    fprintf(stderr, "msolve: -npb %d ignored for this algorithm: a Jacobi block is one GPU (strip) here\n", npb);
+    npb = 1;
+  }
+  const int njacobi = nblocks;
+  nblocks *= npb; /* engines */
   if (nblocks > MSP_MAX_BLOCKS) { fprintf(stderr, "msolve: too many blocks\n"); return 2; }
   const int uses_s = !(alg == MSP_ALG_SM || alg == MSP_ALG_AM || alg == MSP_ALG_GMRES);
 
@@ -170,7 +178,7 @@ int main(int argc, char **argv) {
      * command lines always give identical values; differing sets are rejected instead of silently merged. */
     if (ksp_from_options(&db, "inner_", &inner)) return 2;
     msp_ksp_opts first = inner;
-    for (int k = 1; k <= nblocks; k++) {
+    for (int k = 1; k <= njacobi; k++) {
       char pre[32];
       snprintf(pre, sizeof pre, "inner%d_", k);
       msp_ksp_opts o = inner;
@@ -215,9 +223,9 @@ int main(int argc, char **argv) {
   msp_problem prob;
   memset(&prob, 0, sizeof prob);
   prob.dim = p > 1 ? 3 : 2; prob.m = m; prob.n = n; prob.p = p; prob.nblocks = nblocks;
-  prob.s = uses_s ? s : 0; prob.max_restart = inner.restart; prob.keep_csr = 0;
+  prob.s = uses_s ? s : 0; prob.max_restart = inner.restart; prob.keep_csr = 0; prob.npb = npb;
 
-  if (alg == MSP_ALG_GMRES) {
+  if (alg == MSP_ALG_GMRES && nblocks == 1) {
     /* gmres_solution.c:50-85 */
     msp_engine *e = NULL;
     msp_result res;
@@ -260,6 +268,7 @@ int main(int argc, char **argv) {
     }
   }
   so.alg = alg; so.s = uses_s ? s : 0; so.rtol = rtol; so.inner = inner; so.max_outer = max_outer; so.record_history = 1;
+  if (alg == MSP_ALG_GMRES && opt_find(&db, "-ksp_rtol", NULL) == NULL) so.inner.rtol = 1e-5;
   so.outer_type = outer_type; so.outer_max_it = outer_max_it; so.outer_rtol = outer_rtol; so.outer_abstol = outer_atol;
   so.profile = opt_flag(&db, "-log_view"); /* per-event device times, like PETSc's -log_view (events bracket every launch) */
   for (int k = 0; k < nblocks; k++) so.period[k] = periods[k];
@@ -269,15 +278,31 @@ int main(int argc, char **argv) {
   clock_gettime(CLOCK_MONOTONIC, &ts1);
   const double solve_wall_s = (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec);
 
+  if (alg == MSP_ALG_GMRES) {
+    /* gmres_solution.c:78-85 with the matrix spread over -npb GPUs */
+    printf("Elapsed time (iterations):   %f  seconds \n", res[0].elapsed_s);
+    printf("======================== \n");
+    printf("Number of iterations of GMRES : %d \n", res[0].gmres_its);
+    printf("Right hand side norm : %e \n", res[0].norm0);
+    printf("GMRES residual norm : %e \n", res[0].gmres_rnorm);
+    printf("||r(i)||/||b|| : %e \n", res[0].gmres_rnorm / res[0].norm0);
+    printf("======================== \n");
+    printf("Erreur : %e \n", res[0].error);
+    printf("[msolve] alg=%s gpus_per_block=%d rel_residual=%e\n", algname, npb, res[0].final_residual / res[0].norm0);
+    free(res);
+    msp_group_destroy(g);
+    return 0;
+  }
   printf("Global norm of b %e \n", res[0].norm0); /* …multisplitting.c:157 */
   if (opt_flag(&db, "-print_history"))
     for (int i = 0; i < res[0].hist_len; i++) printf("Final residual norm 2 = %e \n", res[0].hist[i]); /* …multisplitting.c:195 */
   double elapsed = 0.0;
   for (int k = 0; k < nblocks; k++) if (res[k].elapsed_s > elapsed) elapsed = res[k].elapsed_s;
   printf("Elapsed time (iterations):   %f  seconds \n", elapsed); /* utils.c:671 */
-  for (int k = 0; k < nblocks; k++) {
-    if (uses_s) printf("[ Block rank %d ] Total number of iterations (outer_iterations * s) = %d * %d = %d \n", k, res[k].outer_its, s, s * res[k].outer_its); /* utils.c:727 */
-    else printf("[ Block rank %d ] Total number of iterations (outer_iterations) = %d \n", k, res[k].outer_its); /* utils.c:706 */
+  for (int k = 0; k < njacobi; k++) { /* one line per Jacobi block (its first strip when a block spans -npb GPUs) */
+    const msp_result *rk = &res[k * npb];
+    if (uses_s) printf("[ Block rank %d ] Total number of iterations (outer_iterations * s) = %d * %d = %d \n", k, rk->outer_its, s, s * rk->outer_its); /* utils.c:727 */
+    else printf("[ Block rank %d ] Total number of iterations (outer_iterations) = %d \n", k, rk->outer_its); /* utils.c:706 */
   }
   printf("Final residual norm 2 = %e \n", res[0].final_residual); /* utils.c:699 */
   printf("Erreur : %e \n", res[0].error);                        /* …multisplitting.c:229 */
@@ -302,7 +327,7 @@ int main(int argc, char **argv) {
   }
   long long launches = 0;
   for (int k = 0; k < nblocks; k++) launches += (long long)res[k].kernel_launches;
-  printf("[msolve] alg=%s blocks=%d gpus=%d rel_residual=%e kernel_launches=%lld\n", algname, nblocks, ngpu,
+  printf("[msolve] alg=%s blocks=%d gpus=%d rel_residual=%e kernel_launches=%lld\n", algname, njacobi, ngpu,
          res[0].final_residual / res[0].norm0, launches);
   free(res);
   msp_group_destroy(g);

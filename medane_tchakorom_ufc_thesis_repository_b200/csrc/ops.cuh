@@ -5,9 +5,11 @@
 // ------------------------------------------------------------------------------------------------
 static int op_update_rhs(msp_engine *e) {
   if (e->nbrow == 0) return 0;
+  // rhs_K = b_K - A_KJ x_J: only the neighbours that belong to ANOTHER Jacobi block (with npb > 1 a neighbour strip of my own
+  // block is part of A_KK)
   k_update_rhs<<<grid_for(e->nbrow), MSPK_THREADS, 0, e->st>>>(e->nbrow, e->brow, e->nb, e->W, e->H, e->ld, e->ecol, e->eval,
-                                                               e->has_nb[0] ? e->halo[0] : nullptr, e->has_nb[1] ? e->halo[1] : nullptr,
-                                                               e->b, e->rhs);
+                                                               (e->has_nb[0] && !e->intra[0]) ? e->halo[0] : nullptr,
+                                                               (e->has_nb[1] && !e->intra[1]) ? e->halo[1] : nullptr, e->b, e->rhs);
   e->launches++;
   return 0;
 }
@@ -18,6 +20,10 @@ static int op_resid_sumsq(msp_engine *e, bool strip, int dsc_slot) {
   a.b = strip ? e->b : e->rhs;
   if (strip) {
     a.lo = e->has_nb[0] ? e->halo[0] : nullptr; a.hi = e->has_nb[1] ? e->halo[1] : nullptr;
+    launch_spmv_w<1, true, false, true>(e, a, 1, nullptr);
+  } else if (e->npb > 1) {
+    // A_KK of a block spread over several GPUs: the couplings to the strips of my own block count (x halos of the last exchange)
+    a.lo = e->intra[0] ? e->halo[0] : nullptr; a.hi = e->intra[1] ? e->halo[1] : nullptr;
     launch_spmv_w<1, true, false, true>(e, a, 1, nullptr);
   } else {
     launch_spmv_w<0, true, false, true>(e, a, 1, nullptr);
@@ -32,6 +38,126 @@ static int read_scalars(msp_engine *e, int first, int n) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// A Jacobi block spread over npb GPUs (the reference's -npb > 1: comm_jacobi_block of npb ranks, PETSc's MatMult_MPIAIJ
+// scatter + VecMDot_MPI / VecNorm_MPI allreduces inside KSPSolve).  Each GPU owns one strip of the block.
+//  * before every SpMV the boundary layers of the vector being multiplied travel to the block's neighbouring strips
+//    (P2P stores into their windows + neighbour flags, like the x exchange; the layers are published already scaled);
+//  * the MDot results and the sum of squares of the new basis vector are summed over the block's communicator, then a
+//    one-thread kernel closes the step — every GPU of the block keeps an identical copy of the GMRES control state;
+//  * everything is still decided on the device: the host only enqueues.
+// ------------------------------------------------------------------------------------------------
+static int exchange_intra(msp_engine *e, const double *v, const double *scale, int guard_it) {
+  if (!e->intra[0] && !e->intra[1]) return 0;
+  const int par = e->vpar;
+  double *p_lo = e->intra[0] ? e->peer[0].vhalo(1, par) : nullptr; // my first layer is the lower strip's upper halo
+  double *p_hi = e->intra[1] ? e->peer[1].vhalo(0, par) : nullptr;
+  k_publish_boundary_scaled<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->nb, e->H, v, scale, e->ctl, guard_it, p_lo, p_hi);
+  e->launches++;
+  StreamWaitValue64Fn wait = e->bcomm->neighbour_flags() ? stream_wait_value64() : nullptr;
+  if (wait) {
+    const unsigned long long seq = ++e->vex_seq;
+    unsigned long long *f_lo = e->intra[0] ? e->peer[0].flags() + 3 : nullptr;
+    unsigned long long *f_hi = e->intra[1] ? e->peer[1].flags() + 2 : nullptr;
+    k_signal_neighbours<<<1, 32, 0, e->st>>>(f_lo, f_hi, seq);
+    e->launches++;
+    for (int side = 0; side < 2; side++)
+      if (e->intra[side] && wait(e->st, (unsigned long long)(uintptr_t)(e->win.flags() + 2 + side), seq, 0) != 0) MSP_FAIL("cuStreamWaitValue64 failed");
+  } else {
+    RC(e->bcomm->barrier(e->st));
+  }
+  e->vpar ^= 1;
+  return 0;
+}
+// the layers exchange_intra just delivered
+static const double *intra_lo(const msp_engine *e) { return e->intra[0] ? e->win.vhalo(0, e->vpar ^ 1) : nullptr; }
+static const double *intra_hi(const msp_engine *e) { return e->intra[1] ? e->win.vhalo(1, e->vpar ^ 1) : nullptr; }
+
+static int op_inner_solve_dist(msp_engine *e, const msp_ksp_opts *o, bool publish, int *its_out, int *reason_out, double *rnorm_out, bool defer) {
+  if (o->restart < 1 || o->restart > e->prob.max_restart) MSP_FAIL("restart exceeds max_restart of the engine");
+  if (o->mgs) MSP_FAIL("modified Gram-Schmidt is not available for a Jacobi block spread over several GPUs (npb > 1)");
+  defer = defer && !its_out && !reason_out && !rnorm_out && o->max_it <= 4 * o->restart;
+  const bool guess_zero = !o->guess_nonzero;
+  double *bnorm_sq = nullptr;
+  if (!guess_zero && !o->initial_rtol) {
+    k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->rhs, 0.0, e->ws, 2, e->dsc + 8);
+    e->launches++;
+    RC(e->bcomm->allreduce_sum(e->dsc + 8, 1, e->st));
+    bnorm_sq = e->dsc + 8;
+  }
+  k_ctl_begin<<<1, 32, 0, e->st>>>(e->ctl, o->restart, o->max_it, o->min_it, o->initial_rtol, guess_zero ? 1 : 0, o->cgs_refine, o->rtol,
+                                   o->abstol, o->divtol, bnorm_sq);
+  e->launches++;
+  double *lhh = reinterpret_cast<double *>(reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, lhh));
+  const double *invs = reinterpret_cast<const double *>(reinterpret_cast<const char *>(e->ctl) + offsetof(GmresCtl, inv_arr));
+  int itcount = 0;
+  bool first = true;
+  struct { int its, it, reason, active; } hc{};
+  while (true) {
+    const int nsteps = std::min(o->restart, o->max_it - itcount);
+    double *peer_lo = (publish && e->peer[0].base) ? e->peer[0].halo(1, e->par) : nullptr;
+    double *peer_hi = (publish && e->peer[1].base) ? e->peer[1].halo(0, e->par) : nullptr;
+    // ---- cycle prologue: vtilde_0 = rhs - A_KK x over the whole block
+    if (first && guess_zero) {
+      k_copy<<<grid_for(e->nb / 2), MSPK_THREADS, 0, e->st>>>(e->nb, e->rhs, e->V);
+      k_sumsq<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, e->rhs, 0.0, e->ws, 2, e->dsc + 9);
+      e->launches += 2;
+    } else {
+      RC(exchange_intra(e, e->x, nullptr, -1)); // the block's current iterate on the neighbouring strips
+      SpmvArgs a = spmv_args(e, e->x, e->V);
+      a.b = e->rhs; a.lo = intra_lo(e); a.hi = intra_hi(e);
+      launch_spmv_w<1, true, false, true>(e, a, 0, nullptr);
+      CK(cudaMemcpyAsync(e->dsc + 9, e->ws.partial + 0 * MSPK_MAX_PART + MSPK_MAX_PART - 1, sizeof(double), cudaMemcpyDeviceToDevice, e->st));
+    }
+    RC(e->bcomm->allreduce_sum(e->dsc + 9, 1, e->st));
+    k_ctl_cycle_begin_from<<<1, 32, 0, e->st>>>(e->ctl, e->dsc + 9);
+    e->launches++;
+    for (int it = 0; it < nsteps; it++) {
+      double *w = e->V + (long long)(it + 1) * e->ld;
+      const double *vit = e->V + (long long)it * e->ld;
+      RC(exchange_intra(e, vit, invs + it, it));
+      SpmvArgs a = spmv_args(e, vit, w);
+      a.guard_it = it; a.lo = intra_lo(e); a.hi = intra_hi(e);
+      launch_spmv_w<1, false, true, false>(e, a, 0, nullptr);
+      for (int pass = 0; pass < (o->cgs_refine ? 2 : 1); pass++) {
+        launch_mdot(e, it + 1, e->V, e->ld, w, lhh, -1.0, it, pass, invs);
+        RC(e->bcomm->allreduce_sum(lhh, it + 1, e->st));
+        launch_maxpy<2>(e, it + 1, e->V, e->ld, lhh, w, e->dsc + 10, it, pass, pass, 0, invs);
+        RC(e->bcomm->allreduce_sum(e->dsc + 10, 1, e->st));
+        k_step_end<<<1, 32, 0, e->st>>>(e->ctl, e->dsc + 10, pass, it, pass);
+        e->launches++;
+      }
+    }
+    // ---- KSPGMRESBuildSoln + publication of the new iterate's layers for the exchange of the outer loop
+    k_build_soln_coef<<<1, 32, 0, e->st>>>(e->ctl);
+    UpdateXArgs u{};
+    u.nb = e->nb; u.H = e->H; u.ld = e->ld; u.V = e->V; u.x = e->x; u.ctl = e->ctl; u.peer_lo = peer_lo; u.peer_hi = peer_hi;
+    k_update_x<<<grid_for(e->nb, 8), MSPK_THREADS, 0, e->st>>>(u);
+    e->launches += 2;
+    CK(cudaMemcpyAsync(e->hsc + 32, reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, its), 16, cudaMemcpyDeviceToHost, e->st));
+    first = false;
+    if (defer) {
+      itcount += nsteps;
+      if (itcount >= o->max_it) return 0;
+      continue;
+    }
+    CK(cudaStreamSynchronize(e->st));
+    memcpy(&hc, e->hsc + 32, 16);
+    itcount += hc.it;
+    if (hc.reason) break;
+    if (itcount >= o->max_it) { hc.reason = MSP_DIVERGED_ITS; break; }
+    if (hc.it == 0) { hc.reason = MSP_DIVERGED_BREAKDOWN; break; }
+  }
+  if (its_out) *its_out = hc.its;
+  if (reason_out) *reason_out = hc.reason;
+  if (rnorm_out) {
+    CK(cudaMemcpyAsync(e->hsc + 40, reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, ksp_rnorm), 8, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    *rnorm_out = e->hsc[40];
+  }
+  return 0;
+}
+
 // inner_solver utils.c:950-970 -> KSPSolve_GMRES.  One host synchronisation per
 // restart cycle; inside a cycle every decision is taken on the device.
 // `defer`: when the solve is at most four restart cycles (max_it <= 4 restart) and the caller does not ask for
@@ -40,6 +166,7 @@ static int read_scalars(msp_engine *e, int first, int n) {
 // max_it reached — turns all its launches into no-ops), the iteration count is added to ctl->its_total, and the
 // caller's next stream synchronisation covers it.
 static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, int *its_out, int *reason_out, double *rnorm_out, bool defer = false) {
+  if (e->npb > 1) return op_inner_solve_dist(e, o, publish, its_out, reason_out, rnorm_out, defer);
   defer = defer && !its_out && !reason_out && !rnorm_out && o->max_it <= 4 * o->restart;
   if (o->restart < 1 || o->restart > e->prob.max_restart) MSP_FAIL("restart exceeds max_restart of the engine");
   const bool guess_zero = !o->guess_nonzero;

@@ -128,12 +128,15 @@ def connect_blocks(rank: int, world: int, export_window: Callable[[], bytes], co
     barrier()
 
 
-def make_distributed_engine(m, n, p=1, s=0, max_restart=30, keep_csr=False):
-    """Engine of this rank's block, wired to its neighbours.  Call under torchrun (one rank per GPU)."""
+def make_distributed_engine(m, n, p=1, s=0, max_restart=30, keep_csr=False, npb=1):
+    """Engine of this rank's strip, wired to its neighbours.  Call under torchrun (one rank per GPU).
+    npb = GPUs per Jacobi block (the reference's -npb): Jacobi blocks = WORLD_SIZE / npb, rank r belongs to block r // npb."""
     from . import solver
     rank, world, local = env_rank()
     init_process_group()
-    eng = solver.Engine(m, n, p, block=rank, nblocks=world, s=s, max_restart=max_restart, device=local, keep_csr=keep_csr)
+    if world % npb:
+        raise ValueError("WORLD_SIZE must be a multiple of npb")
+    eng = solver.Engine(m, n, p, block=rank, nblocks=world, s=s, max_restart=max_restart, device=local, keep_csr=keep_csr, npb=npb)
     if world > 1:
         connect_blocks(rank, world, eng.comm_export, eng.comm_connect, solver.comm_unique_id, eng.comm_init,
                        eng.comm_connect_block)

@@ -73,12 +73,13 @@ class Engine:
     """One Jacobi block resident on one GPU (msp_engine)."""
 
     def __init__(self, m, n, p=1, block=0, nblocks=1, s=0, max_restart=30, device=0, keep_csr=False, _handle=None,
-                 _owner=None):
+                 _owner=None, npb=1):
+        """block / nblocks: this GPU's strip and the number of strips; npb: GPUs per Jacobi block (Jacobi blocks = nblocks / npb)."""
         self._owner = _owner
         if _handle is not None:
             self.h = _handle
         else:
-            prob = Problem(3 if p > 1 else 2, m, n, p, block, nblocks, s, max_restart, int(keep_csr))
+            prob = Problem(3 if p > 1 else 2, m, n, p, block, nblocks, s, max_restart, int(keep_csr), int(npb))
             h = C.c_void_p()
             check(_lib.lib().msp_create(C.byref(prob), device, C.byref(h)))
             self.h = h
@@ -351,16 +352,20 @@ class Group:
     (tests) or sit on different GPUs of one box (peer access)."""
 
     def __init__(self, m, n, p=1, nblocks=2, s=0, max_restart=30, devices: Optional[Sequence[int]] = None,
-                 keep_csr=False):
-        prob = Problem(3 if p > 1 else 2, m, n, p, 0, nblocks, s, max_restart, int(keep_csr))
-        devs = (C.c_int * nblocks)(*(devices if devices is not None else [0] * nblocks))
+                 keep_csr=False, npb=1):
+        """nblocks Jacobi blocks of npb GPUs each: nblocks * npb engines (strips), in strip order."""
+        nranks = nblocks * npb
+        prob = Problem(3 if p > 1 else 2, m, n, p, 0, nranks, s, max_restart, int(keep_csr), int(npb))
+        devs = (C.c_int * nranks)(*(devices if devices is not None else [0] * nranks))
         h = C.c_void_p()
-        check(_lib.lib().msp_group_create(C.byref(prob), nblocks, devs, C.byref(h)))
+        check(_lib.lib().msp_group_create(C.byref(prob), nranks, devs, C.byref(h)))
         self.h = h
-        self.nblocks = nblocks
+        self.nblocks = nranks   # engines; Jacobi blocks = nranks / npb
+        self.njacobi_blocks = nblocks
+        self.npb = npb
         self.s = s
-        self.engines = [Engine(m, n, p, k, nblocks, s, max_restart, _handle=C.c_void_p(_lib.lib().msp_group_engine(h, k)),
-                               _owner=self) for k in range(nblocks)]
+        self.engines = [Engine(m, n, p, k, nranks, s, max_restart, _handle=C.c_void_p(_lib.lib().msp_group_engine(h, k)),
+                               _owner=self) for k in range(nranks)]
 
     def close(self):
         if getattr(self, "h", None):

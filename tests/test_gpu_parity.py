@@ -884,6 +884,49 @@ def test_group_abort_reports_the_failing_block(S):
     grp.close()
 
 
+@pytest.mark.parametrize("alg,dims,G,npb,s,max_it", [("SMSM_GLOBAL", (48, 40, 1), 2, 2, 4, 5), ("SM", (48, 32, 1), 2, 3, 0, 20),
+                                                     ("SMSM_GLOBAL", (12, 12, 16), 2, 4, 5, 5), ("SMSM_GLOBAL", (64, 48, 1), 1, 4, 5, 20),
+                                                     ("SMSM_GLOBAL", (48, 40, 1), 4, 2, 10, 5)])
+def test_jacobi_block_over_several_gpus(S, oracle, alg, dims, G, npb, s, max_it):
+    """SURVEY §8 f4, the reference's -npb > 1: every Jacobi block is spread over npb strips (GPUs) and its inner GMRES runs
+    distributed over them (Krylov-vector layers between the strips, MDot / norm sums over the block's communicator).  The
+    algorithm only depends on the number of Jacobi blocks: the iterates must equal the oracle's with nblocks = G."""
+    m, n, p = dims
+    inner = dict(restart=30, max_it=max_it, rtol=1e-10, abstol=1e-100)
+    grp = S.Group(m, n, p, nblocks=G, npb=npb, s=s, max_restart=30)
+    assert len(grp.engines) == G * npb
+    res = grp.solve(alg, s=s, rtol=1e-300, inner=S.ksp_opts(**inner), max_outer=2)
+    ref = oracle.solve(alg, m, n, p=p, nblocks=G, s=s, rtol=1e-300, inner=inner, max_outer=2)
+    x = grp.solution()
+    tight = max_it <= 5 or alg == "SM" or G == 1
+    assert np.linalg.norm(x - ref["x"]) <= (1e-8 if tight else 1e-6) * np.linalg.norm(ref["x"])
+    assert np.allclose(res[0]["hist"], ref["hist"], rtol=1e-6 if tight else 1e-2)
+    assert all(r["inner_its_total"] == res[0]["inner_its_total"] for r in res)  # identical control state on every strip
+    grp.close()
+    grp = S.Group(m, n, p, nblocks=G, npb=npb, s=s, max_restart=30)
+    res = grp.solve(alg, s=s, rtol=1e-6, inner=S.ksp_opts(**inner), max_outer=5000)
+    ref = oracle.solve(alg, m, n, p=p, nblocks=G, s=s, rtol=1e-6, inner=inner, max_outer=5000)
+    assert abs(res[0]["outer_its"] - ref["outer_its"]) <= 1, (res[0]["outer_its"], ref["outer_its"])
+    assert res[0]["final_residual"] <= 1e-6 * res[0]["norm0"] * 1.0000001
+    grp.close()
+
+
+def test_standalone_gmres_over_several_gpus(S, oracle):
+    """gmres_solution.c with the matrix spread over 4 strips (the reference runs it on `mpirun -n NP`): same iteration
+    count and solution as the oracle's single-process GMRES; restart shorter than the run, so several cycles."""
+    N = 48
+    rp, ci, va = oracle.poisson2d_complete(N, N)
+    b = oracle.spmv(rp, ci, va, np.ones(N * N))
+    for restart, refine in ((30, 0), (12, 0), (30, 1)):
+        x, its, reason, rnorm = oracle.gmres(rp, ci, va, b, restart=restart, max_it=2000, rtol=1e-8, abstol=1e-100, initial_rtol=1, cgs_refine=refine)
+        grp = S.Group(N, N, nblocks=1, npb=4, max_restart=30)
+        res = grp.solve("GMRES", inner=S.ksp_opts(restart=restart, max_it=2000, rtol=1e-8, abstol=1e-100, initial_rtol=1, cgs_refine=refine))
+        assert all(abs(r["gmres_its"] - its) <= 1 and r["gmres_reason"] == reason for r in res), ([r["gmres_its"] for r in res], its)
+        assert np.linalg.norm(grp.solution() - x) <= 1e-6 * np.linalg.norm(x)
+        assert abs(res[0]["final_residual"] - res[0]["gmres_rnorm"]) <= 1e-6 * res[0]["norm0"]
+        grp.close()
+
+
 def test_pipelined_host_transfers(S):
     """msp_set_b_async / msp_set_x_async / msp_get_x_async / msp_copies_wait (the e2e path of bench.py): same numbers as
     the blocking calls; the download is a snapshot, so the next upload cannot tear it."""
