@@ -242,7 +242,7 @@ def parity_check(world):
     return out
 
 
-def time_to_rtol_leg(args, world):
+def time_to_rtol_leg(args, world, npb=1):
     """BASELINE.json's metric, measured: SMSM global minimisation to rtol 1e-6 on the 3-D 7-point Poisson 512^3 problem
     (north_star), one block per GPU, timed like the reference times it (device time of the outer loop after assembly,
     barrier on both sides, …-global.c:284-286,365-366), max over ranks.  `reached` is decided on the TRUE residual
@@ -250,10 +250,10 @@ def time_to_rtol_leg(args, world):
     from medane_tchakorom_ufc_thesis_repository_b200 import distributed as D
     from medane_tchakorom_ufc_thesis_repository_b200 import solver as S
     N, s = args.ttr_grid, args.ttr_s
-    if N % world:
-        return {"skipped": f"{N} planes do not divide over {world} blocks"}
+    if N % world or world % npb:
+        return {"skipped": f"{N} planes do not divide over {world} GPUs in blocks of {npb}"}
     rank, _, local = D.env_rank()
-    eng = D.make_distributed_engine(N, N, N, s=s, max_restart=TTR["inner"]["restart"])
+    eng = D.make_distributed_engine(N, N, N, s=s, max_restart=TTR["inner"]["restart"], npb=npb)
     inner = S.ksp_opts(**TTR["inner"])
     sampler = ClockSampler(local)
     D.barrier()
@@ -270,7 +270,8 @@ def time_to_rtol_leg(args, world):
             "stopping_quantity_rel": float(res["last_norm"] / res["norm0"]),
             "stop_reason": {0: "converged", 1: "max_outer", 2: "max_seconds"}[res["stop_reason"]],
             "error_norm": float(res["error"]), "gpu_launches": launches, "clocks": clocks,
-            "workload": f"SMSM_GLOBAL s={s}, 3-D 7-pt Poisson {N}^3 ({N ** 3} rows), {world} block(s) = GPU(s), "
+            "jacobi_blocks": world // npb, "gpus_per_block": npb,
+            "workload": f"SMSM_GLOBAL s={s}, 3-D 7-pt Poisson {N}^3 ({N ** 3} rows), {world // npb} Jacobi block(s) x {npb} GPU(s) per block, "
                         f"inner GMRES(30) max_it {TTR['inner']['max_it']} rtol 1e-10 UIR, exact LS (TSQR), rtol 1e-6, x0 = 0"}
 
 
@@ -408,6 +409,12 @@ def run_gpu(args):
         line["parity_check"] = parity
     if not args.no_time_to_rtol:
         line["time_to_rtol"] = time_to_rtol_leg(args, world)
+        if world >= 4:
+            # the reference's own topology: exactly two Jacobi blocks (iSolve:332-338), each spread over -npb = N/2 GPUs
+            line["time_to_rtol_two_blocks"] = time_to_rtol_leg(args, world, npb=world // 2)
+        if world >= 2:
+            # one Jacobi block over all GPUs (-npb N): no block-Jacobi penalty, every Arnoldi step pays two small allreduces
+            line["time_to_rtol_one_block"] = time_to_rtol_leg(args, world, npb=world)
     if rank == 0 and not args.no_cpu_baseline and world == 1 and args.alg == "SMSM_GLOBAL" and args.p == 1:
         line["cpu_baseline"] = cpu_baseline(args)
     if rank == 0:
@@ -446,7 +453,7 @@ def run_to_rtol(args):
     n = args.to_rtol
     p = n if args.p > 1 else 1
     sb = args.s_basis
-    eng = D.make_distributed_engine(n, n, p, s=sb, max_restart=INNER["restart"])
+    eng = D.make_distributed_engine(n, n, p, s=sb, max_restart=INNER["restart"], npb=args.npb)
     inner = S.ksp_opts(**dict(INNER, max_it=args.inner_max_it))
     sampler = ClockSampler(local)
     D.barrier()
@@ -463,7 +470,7 @@ def run_to_rtol(args):
         grid = f"3-D 7-pt Poisson {n}^3" if p > 1 else f"2-D 5-pt Poisson {n}x{n}"
         print(json.dumps({
             "metric": "time_to_rtol_1e-6", "value": t_dev, "unit": "s", "n_gpus": world, "higher_is_better": False, "dtype": "f64",
-            "config": {"workload": f"{args.alg} s={sb}, {grid}, {world} block(s), inner GMRES(30) max_it {args.inner_max_it} rtol 1e-10"},
+            "config": {"workload": f"{args.alg} s={sb}, {grid}, {world // args.npb} Jacobi block(s) x {args.npb} GPU(s), inner GMRES(30) max_it {args.inner_max_it} rtol 1e-10"},
             "outer_its": its, "reached": bool(res["final_residual"] <= RTOL * res["norm0"] * 1.000001),
             "true_rel_residual_after_closing_exchange": res["final_residual"] / res["norm0"],
             "stopping_quantity_rel": res["last_norm"] / res["norm0"], "error_norm": res["error"],
@@ -531,6 +538,7 @@ def _main():
     ap.add_argument("--ttr-grid", type=int, default=TTR["grid"])
     ap.add_argument("--ttr-s", type=int, default=TTR["s"])
     ap.add_argument("--ttr-max-seconds", type=float, default=150.0)
+    ap.add_argument("--npb", type=int, default=1, help="GPUs per Jacobi block for --to-rtol runs (the reference's -npb; Jacobi blocks = N / npb)")
     ap.add_argument("--basis-size", dest="s_basis", type=int, default=S_BASIS,
                     help="minimisation basis size s for --to-rtol runs (not `--s`: torchrun's parser takes it for a prefix of its own options)")
     ap.add_argument("--to-rtol", type=int, default=0, help="run --alg to rtol 1e-6 on an N x N (x N with --grid-depth > 1) grid and report seconds")

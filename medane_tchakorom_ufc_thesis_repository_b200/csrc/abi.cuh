@@ -534,6 +534,10 @@ int msp_comm_init(msp_engine *e, const void *id128, int rank, int nranks) {
     if (rc) { delete b; MSP_FAIL(std::string("ncclCommSplit: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?")); }
     e->bcomm = b; e->own_bcomm = true;
   }
+  // first collective of a communicator sets up its peer connections (tens of milliseconds): here, not inside a timed solve
+  RC(e->comm->barrier(e->st));
+  if (e->bcomm != e->comm) RC(e->bcomm->barrier(e->st));
+  CK(cudaStreamSynchronize(e->st));
   return 0;
 }
 int msp_comm_export(msp_engine *e, void *handle64) {
