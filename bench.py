@@ -226,16 +226,29 @@ def parity_check(world):
     asy_its = [int(v) for v in D.allgather_bytes(str(asy["outer_its"]).encode())]
     eng.close()
     D.barrier()
+    # (3) one Jacobi block spread over all GPUs (-npb = world: distributed inner GMRES, block communicator): the iterates
+    #     depend on the number of Jacobi blocks only, so this must reproduce the ONE-block fixture
+    fx1 = np.load(os.path.join(ROOT, "tests", "golden", "bench_parity_G1.npz"))
+    eng = D.make_distributed_engine(64, 64, 1, s=5, max_restart=30, npb=world)
+    res1 = eng.solve("SMSM_GLOBAL", s=5, rtol=1e-300, inner=inner, max_outer=3)
+    parts = D.allgather_bytes(eng.x.tobytes())
+    x1 = np.concatenate([np.frombuffer(b, dtype=np.float64) for b in parts])
+    dx1 = float(np.linalg.norm(x1 - fx1["x3"]) / np.linalg.norm(fx1["x3"]))
+    dh1 = float(np.max(np.abs(res1["hist"] / fx1["hist3"] - 1.0)))
+    eng.close()
+    D.barrier()
     # the asynchronous detection protocol bounds every block's LOCAL residual by rtol / sqrt(G) over a pseudo-period
     # (conv_detection_prime.c:11-249); what the global residual is after the closing exchange depends on the interleaving:
     # a small multiple of rtol (measured 1.5e-6 .. 6e-6 here; the oracle's simulated schedules give up to 17 x rtol)
     asy_ok = asy["stop_reason"] == 0 and asy_rel <= 100.0 * 1e-6
-    ok = dx <= 1e-8 and dh <= 1e-8 and abs(its_delta) <= 1 and asy_ok
+    ok = dx <= 1e-8 and dh <= 1e-8 and abs(its_delta) <= 1 and asy_ok and dx1 <= 1e-8 and dh1 <= 1e-8
     out = {"ok": bool(ok), "blocks": world,
            "cases": {"SMSM_GLOBAL 64x64 s=5, 3 outer iterations vs oracle fixture": {"max_dx": dx, "max_dhist": dh},
                      "SMSM_GLOBAL 64x64 s=5 to rtol 1e-6": {"outer_its": int(full["outer_its"]), "oracle_outer_its": int(fx["outer_its_to_1e6"]), "its_delta": its_delta},
                      "AMAM_GLOBAL 64x64 s=5 free-running to rtol 1e-6": {"true_rel_residual": asy_rel, "outer_its_per_block": asy_its,
-                                                                          "all_blocks_finished_by_protocol": bool(asy["stop_reason"] == 0)}},
+                                                                          "all_blocks_finished_by_protocol": bool(asy["stop_reason"] == 0)},
+                     f"SMSM_GLOBAL 64x64 s=5, ONE Jacobi block over {world} GPUs (-npb {world}), 3 outer iterations vs the one-block oracle fixture":
+                         {"max_dx": dx1, "max_dhist": dh1}},
            "max_dx": dx, "its_delta": its_delta}
     if rank == 0 and not ok:
         sys.stderr.write("bench.py: parity_check FAILED: " + json.dumps(out) + "\n")

@@ -927,6 +927,30 @@ def test_standalone_gmres_over_several_gpus(S, oracle):
         grp.close()
 
 
+def test_msolve_npb_option(S, oracle):
+    """The C driver's -npb: 2 Jacobi blocks x 2 strips each (4 engines on this GPU) give the oracle's 2-block iteration count;
+    the stand-alone GMRES binary spread over 4 strips gives the single-process count."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "bin", "msolve")
+    common = ["-inner_ksp_max_it", "5", "-inner_ksp_rtol", "1e-10", "-inner_ksp_atol", "1e-100", "-inner_ksp_gmres_restart", "30"]
+    out = subprocess.run([exe, "-alg", "SMSM_GLOBAL", "-npb", "2", "-m", "32", "-n", "32", "-rtol", "1e-6", "-s", "5"] + common,
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    ref = oracle.solve("SMSM_GLOBAL", 32, 32, nblocks=2, s=5, rtol=1e-6, inner=dict(restart=30, max_it=5, rtol=1e-10, abstol=1e-100))
+    its = [int(v) for v in re.findall(r"\[ Block rank \d \] Total number of iterations \(outer_iterations \* s\) = (\d+) \* 5", out.stdout)]
+    assert len(its) == 2 and all(abs(i - ref["outer_its"]) <= 1 for i in its), out.stdout
+    out = subprocess.run([exe, "-alg", "gmres_solution", "-npb", "4", "-m", "32", "-n", "32", "-ksp_rtol", "1e-6", "-ksp_atol", "1e-100",
+                          "-ksp_max_it", "100000", "-ksp_converged_use_initial_residual_norm", "-ksp_gmres_restart", "30"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rp, ci, va = oracle.poisson2d_complete(32, 32)
+    b = oracle.spmv(rp, ci, va, np.ones(1024))
+    _, gits, _, _ = oracle.gmres(rp, ci, va, b, restart=30, rtol=1e-6, abstol=1e-100, max_it=100000, initial_rtol=1)
+    assert abs(int(re.search(r"Number of iterations of GMRES : (\d+)", out.stdout).group(1)) - gits) <= 1
+
+
 def test_pipelined_host_transfers(S):
     """msp_set_b_async / msp_set_x_async / msp_get_x_async / msp_copies_wait (the e2e path of bench.py): same numbers as
     the blocking calls; the download is a snapshot, so the next upload cannot tear it."""
