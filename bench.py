@@ -1,20 +1,22 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the multisplitting solve path (contract: see the task statement).
 
-Workload (BASELINE.json configs[2]): SMSM global minimisation, s = 5, 2-D 5-point Poisson 8192 x 8192,
+Workload of `value` (BASELINE.json configs[2]): SMSM global minimisation, s = 5, 2-D 5-point Poisson 8192 x 8192,
 inner GMRES(30) capped at max_it 20 (rtol 1e-10, initial-residual norm), exact least-squares minimiser
 (TSQR), one Jacobi block per GPU (1-D strip partition), fp64, deterministic inputs (b = A 1, x0 = 0).
 
 A "step" is ONE OUTER ITERATION of the reference's do { } while loop (…-minimization-global.c:288-363):
 s x (updateLocalRHS, inner GMRES solve of <= 20 Arnoldi steps, boundary exchange, S[:,t] = x), then
-R = A S, the least-squares solve and x = S alpha.  The time-to-rtol-1e-6 the metric names is
-outer_iterations x (seconds per outer iteration); the oracle shows this configuration needs ~3e3 outer
-iterations at one block (x3.2 per doubling of the edge: 939 measured at 4096^2), i.e. far longer than a benchmark run, so the
-bench times K outer iterations and reports seconds per outer iteration (strong scaling: the problem is
-fixed, blocks = GPUs).  `--to-rtol` runs the real thing to convergence on a smaller grid.
+R = A S, the least-squares solve and x = S alpha.  That configuration needs ~3e3 outer iterations at one block and
+does not converge with several, so `value` is seconds per outer iteration (strong scaling: the problem
+is fixed, blocks = GPUs) and the metric BASELINE.json names — time to rtol 1e-6 — is MEASURED on the north_star
+problem in the same run: `time_to_rtol` = SMSM global, s = 20, 3-D 7-point Poisson 512^3, one Jacobi block per GPU,
+to a true relative residual <= 1e-6 (plus, for N >= 4, the reference's own topology of two Jacobi blocks x N/2 GPUs
+and, for N >= 2, one Jacobi block over all GPUs: `time_to_rtol_two_blocks`, `time_to_rtol_one_block`).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N --steps K ...   # CPU restatement of the reference on host cores
+  python bench.py --impl reference --gpus N --steps K ...   # CPU restatement of the reference, same size, host cores
+  python bench.py --to-rtol 512 --grid-depth 512 --alg SMSM_GLOBAL --basis-size 20 [--npb P]   # one time-to-rtol run
 """
 from __future__ import annotations
 
