@@ -410,8 +410,9 @@ def _golden_runs():
 @pytest.mark.parametrize("g", _golden_runs(), ids=lambda g: f"{g['alg']}-{g['m']}x{g['n']}x{g.get('p', 1)}-G{g['nblocks']}-it{g['inner']['max_it']}")
 def test_sync_driver_parity(S, oracle, g):
     """Two checks per configuration.
-    (a) the first two outer iterations, value for value: 1e-8 relative on x (north_star) — this is where "same
-        algorithm, same arithmetic" is decidable.
+    (a) the first two outer iterations, value for value: 1e-10 relative on x where the regime allows it (north_star
+        asks 1e-8; the bars per regime are set from measured margins, see below) — this is where "same algorithm, same
+        arithmetic" is decidable.
     (b) the whole run: outer-iteration count within +-1 of the oracle, and the two solutions within the run's own
         stopping tolerance of each other.  A tighter bar on (b) is not meaningful: minimising over nearly collinear
         iterates amplifies ANY rounding-level difference (here: the order of the fp64 reductions) by 30x..1e4x per
@@ -424,13 +425,18 @@ def test_sync_driver_parity(S, oracle, g):
     ref = oracle.solve(g["alg"], g["m"], g["n"], **dict(args, rtol=1e-300), max_outer=2)
     assert res[0]["outer_its"] == ref["outer_its"] == 2
     x = grp.solution()
+    # Three regimes, bars = about ten times the deviation measured on a B200 (profiles/r02_parity_margins.txt, tools/parity_margins.py),
+    # never looser than needed and never below what fp64 reductions in a different order can deliver:
+    #  * no minimisation over nearly dependent iterates (MSM, one block) or inexact inner solves (max_it <= 5): measured
+    #    dx <= 6e-13, history <= 6e-12  -> 1e-10 / 1e-9 (north_star asks 1e-8)
+    #  * several blocks with accurate inner solves (max_it 20): the iterates are nearly collinear and the minimiser amplifies
+    #    rounding differences: measured dx <= 6e-8, history <= 2.3e-4 -> 1e-6 / 1e-2
+    #  * the same with a wide basis (s >= 10): 21 nearly dependent columns, the minimal residual itself depends on the
+    #    least-squares solver at the percent level (measured dx 1.5e-7, history 1.4e-2) -> 1e-5 / 1e-1
     well_conditioned = g["alg"] == "SM" or g["nblocks"] == 1 or g["inner"]["max_it"] <= 5
-    # wide basis AND accurate inner solves: 21 nearly dependent columns; the minimal residual itself then depends on the
-    # least-squares solver at the percent level from the first outer iteration on (measured at 48^3, 4 blocks, s = 20:
-    # 2e-4 / 1.4 % on the two history values against the oracle, 1e-3 / 0.5 % against numpy's lstsq)
     wide_accurate = g["s"] >= 10 and not well_conditioned
-    x_bar = 1e-8 if well_conditioned else (1e-3 if wide_accurate else 1e-6)
-    h_bar = 1e-6 if well_conditioned else (5e-2 if wide_accurate else 1e-2)
+    x_bar = 1e-10 if well_conditioned else (1e-5 if wide_accurate else 1e-6)
+    h_bar = 1e-9 if well_conditioned else (1e-1 if wide_accurate else 1e-2)
     assert np.linalg.norm(x - ref["x"]) <= x_bar * np.linalg.norm(ref["x"])
     # semi-local / local: every block reports its own local norm; the oracle's history keeps the worst block
     assert np.allclose(np.max([r["hist"] for r in res], axis=0), ref["hist"], rtol=h_bar)
@@ -445,15 +451,19 @@ def test_sync_driver_parity(S, oracle, g):
     assert abs(its - g["outer_its"]) <= 1, (its, g["outer_its"])
     assert ref["outer_its"] == g["outer_its"]
     x = grp.solution()
+    exact_regime = g["alg"] == "SM" or g["nblocks"] == 1   # measured dx over the WHOLE run <= 1.7e-12 (108 / 130 sweeps, 3 outer iterations)
     if its == ref["outer_its"]:
-        assert np.linalg.norm(x - ref["x"]) <= max(1e-8, 100 * g["rtol"]) * np.linalg.norm(ref["x"])
+        # whole runs: measured dx up to 5.1e-5 at rtol 1e-6 where a minimisation is involved (both iterates sit inside the
+        # stopping tolerance; 51 x rtol for the semi-local run)
+        assert np.linalg.norm(x - ref["x"]) <= (1e-10 if exact_regime else max(1e-8, 100 * g["rtol"])) * np.linalg.norm(ref["x"])
     if g["alg"] in ("SM", "SMSM_GLOBAL"):
         # the stopping quantity is (an estimate of) the global residual: the returned iterate really satisfies it
         assert res[0]["final_residual"] <= g["rtol"] * res[0]["norm0"] * 1.0000001
         if its == ref["outer_its"]:
             # the value at the stopping iteration drifts with the iterates in the ill-conditioned regime (see (b) above:
             # 21 % seen for 32x32 G=2 max_it 20 after a change of nothing but the summation layout of one norm)
-            bar = 0.2 if well_conditioned else 0.5
+            # measured: MSM / one block 4e-10 .. 1e-8; inexact inner solves 8e-6 .. 1.8e-2; accurate inner solves 2e-4 .. 0.23
+            bar = 1e-6 if exact_regime else (0.2 if well_conditioned else 0.5)
             assert abs(res[0]["final_residual"] - ref["final_residual"]) <= bar * ref["final_residual"]
     else:
         # semi-local / local stop on the blocks' local residuals (…-semi-local.c:326-333): same rule, same threshold
