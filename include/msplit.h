@@ -189,7 +189,7 @@ int msp_get_rhs(msp_engine *e, double *rhs);
 
 /* ---- operator surface (include/utils.h) ---- */
 int msp_update_local_rhs(msp_engine *e);                                   /* updateLocalRHS utils.c:943-948 */
-int msp_inner_solve(msp_engine *e, const msp_ksp_opts *o, int *its, int *reason, double *rnorm); /* inner_solver utils.c:950-970 */
+int msp_inner_solve(msp_engine *e, const msp_ksp_opts *o, int *its, int *reason, double *rnorm); /* inner_solver utils.c:950-970; with npb > 1 collective over the GPUs of the block, like KSPSolve on comm_jacobi_block */
 int msp_local_residual_norm(msp_engine *e, double *nrm);  /* ||rhs_K - A_KK x_K||  (…multisplitting.c:187-188) */
 int msp_block_residual_norm(msp_engine *e, double *nrm);  /* ||b_K - A_K,: x||     (computeFinalResidualNorm utils.c:579-580) */
 int msp_error_norm_sq(msp_engine *e, double *sq);         /* computeError utils.c:1045-1059, block part squared */
