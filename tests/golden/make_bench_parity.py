@@ -16,6 +16,7 @@ here = os.path.dirname(os.path.abspath(__file__))
 for G in (1, 2, 4, 8):  # G = 1: what a run with ONE Jacobi block spread over all GPUs (-npb N) must reproduce
     r3 = O.solve("SMSM_GLOBAL", 64, 64, nblocks=G, s=5, rtol=1e-300, inner=inner, max_outer=3)
     rf = O.solve("SMSM_GLOBAL", 64, 64, nblocks=G, s=5, rtol=1e-6, inner=inner, max_outer=5000, want_x=False)
+    r5 = O.solve("SMSM_GLOBAL", 64, 64, nblocks=G, s=5, rtol=1e-5, inner=inner, max_outer=5000, want_x=False)
     np.savez(os.path.join(here, f"bench_parity_G{G}.npz"), x3=r3["x"], hist3=r3["hist"], norm0=r3["norm0"],
-             outer_its_to_1e6=rf["outer_its"], final_rel=rf["final_residual"] / rf["norm0"])
-    print(G, r3["hist"], rf["outer_its"])
+             outer_its_to_1e6=rf["outer_its"], outer_its_to_1e5=r5["outer_its"], final_rel=rf["final_residual"] / rf["norm0"])
+    print(G, r3["hist"], rf["outer_its"], r5["outer_its"])
