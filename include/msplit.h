@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define MSP_VERSION 100
+#define MSP_VERSION 200 /* round 2: msp_problem.npb, msp_solve_opts.{max_seconds,detector,...}, msp_result.{hist_dropped,stop_reason} */
 #define MSP_MAX_RESTART 64
 #define MSP_MAX_S 32
 #define MSP_MAX_BLOCKS 64

@@ -28,7 +28,7 @@ def test_library_loads_and_exports_header_symbols():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for sym in declared:
         assert hasattr(L, sym), sym
-    assert L.msp_version() == 100
+    assert L.msp_version() == 200
 
 
 def test_no_cpu_fallback_message(tmp_path, monkeypatch):

@@ -561,6 +561,18 @@ def test_legacy_counter_detector(S, alg, s, G, periods):
     grp.close()
 
 
+def test_async_driver_is_profiled(S):
+    """the asynchronous driver fills the per-class profile (CUDA events around every hot launch) like
+    the synchronous one, so AMAM bench lines carry a real roofline."""
+    grp = S.Group(64, 64, nblocks=2, s=3, max_restart=30)
+    res = grp.solve("AMAM_GLOBAL", s=3, rtol=1e-4, inner=S.ksp_opts(restart=30, max_it=5, rtol=1e-10, abstol=1e-100), max_outer=20000, profile=True)
+    for r in res:
+        assert r["stop_reason"] == 0
+        for cls in ("spmv", "mdot", "maxpy"):
+            assert r["prof"][cls]["launches"] > 0 and r["prof"][cls]["ms"] > 0 and r["prof"][cls]["bytes"] > 0
+    grp.close()
+
+
 def test_time_to_rtol_1024_one_block(S):
     """The metric as BASELINE.json names it (SMSM time-to-rtol 1e-6), on a grid where it is reachable: 1024x1024, one
     block; outer-iteration count against the oracle run recorded in tests/golden/smsm_global_1024_to_rtol.json."""
