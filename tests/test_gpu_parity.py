@@ -1025,6 +1025,20 @@ def test_isolve_launcher(S):
     assert "Elapsed time (iterations):" in out.stdout and "Final residual norm 2 =" in out.stdout
 
 
+def test_isolve_np_npb_like_the_reference(S, oracle):
+    """iSolve --np 4 --npb 2: four ranks, two per Jacobi block, i.e. the reference's 2-block topology with every block spread
+    over two strips; same sweep count as the oracle's two-block MSM."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([os.path.join(root, "iSolve"), "--alg", "SM", "--np", "4", "--npb", "2", "--m", "32", "--n", "32", "--rtol", "1e-5",
+                          "--inner-max-it", "20", "--inner-rtol", "1e-10"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    its = [int(v) for v in re.findall(r"\[ Block rank \d \] Total number of iterations \(outer_iterations\) = (\d+)", out.stdout)]
+    ref = oracle.solve("SM", 32, 32, nblocks=2, s=0, rtol=1e-5, inner=dict(restart=30, max_it=20, rtol=1e-10, abstol=1e-100))
+    assert len(its) == 2 and all(abs(i - ref["outer_its"]) <= 1 for i in its), (its, ref["outer_its"], out.stdout)
+
+
 def test_errors(S):
     with pytest.raises(S.MsplitError):
         S.Engine(10, 10, nblocks=3)  # grid lines not divisible by the block count
