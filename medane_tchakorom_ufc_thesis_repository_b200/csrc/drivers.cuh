@@ -41,6 +41,8 @@ struct MinimizeOpts { int outer_type, max_it; double rtol, abstol; };
 static int op_minimize(msp_engine *e, int alg, int s, const MinimizeOpts &mo, double *alpha, double *norm_out, int *lits_out) {
   const int G = e->prob.nblocks;
   const bool global = (alg == MSP_ALG_SMSM_GLOBAL);
+  if (e->npb > 1 && !global && mo.outer_type != 0)
+    MSP_FAIL("with npb > 1 the (semi-)local minimisation is solved exactly (TSQR over the block's GPUs); LSQR / CG / normal equations run block-local with npb = 1 only");
   double norm = 0.0;
   int lits = 0;
   if (mo.outer_type == 1) {
@@ -62,6 +64,16 @@ static int op_minimize(msp_engine *e, int alg, int s, const MinimizeOpts &mo, do
       CK(cudaMemcpyAsync(all.data(), e->dfac, sizeof(double) * (size_t)G * nn, cudaMemcpyDeviceToHost, e->st));
       CK(cudaStreamSynchronize(e->st));
       RC(tsqr_combine(s, G, all.data(), alpha, &norm));
+    } else if (!global && e->npb > 1) {
+      // (semi-)local least squares of a Jacobi block spread over npb GPUs: the TSQR tree of the block's strips only
+      const int P = e->npb, nn = (s + 1) * (s + 1);
+      std::vector<double> all((size_t)P * nn, 0.0);
+      memcpy(all.data() + (size_t)(e->prob.block % P) * nn, uaug.data(), sizeof(double) * nn);
+      CK(cudaMemcpyAsync(e->dfac, all.data(), sizeof(double) * (size_t)P * nn, cudaMemcpyHostToDevice, e->st));
+      RC(e->bcomm->allreduce_sum(e->dfac, P * nn, e->st));
+      CK(cudaMemcpyAsync(all.data(), e->dfac, sizeof(double) * (size_t)P * nn, cudaMemcpyDeviceToHost, e->st));
+      CK(cudaStreamSynchronize(e->st));
+      RC(tsqr_combine(s, P, all.data(), alpha, &norm));
     } else {
       RC(tsqr_combine(s, 1, uaug.data(), alpha, &norm));
     }
@@ -102,8 +114,6 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
   msp_ksp_opts in = o->inner;
   in.initial_rtol = 1; in.guess_nonzero = 1; // inner_solver utils.c:956-957
   if (alg != MSP_ALG_SM && (s < 1 || s > e->smax)) MSP_FAIL("s exceeds the engine's basis storage");
-  if (e->npb > 1 && alg != MSP_ALG_SM && alg != MSP_ALG_SMSM_GLOBAL)
-    MSP_FAIL("a Jacobi block spread over several GPUs (npb > 1) is supported by SM, SMSM_GLOBAL and the stand-alone GMRES");
   const int max_outer = o->max_outer > 0 ? o->max_outer : 1000000;
   memset(res, 0, sizeof(*res));
   // global_norm_0 = computeFinalResidualNorm(x = 0) before the loop (…multisplitting.c:162) = ||b||; computed from b so
@@ -113,7 +123,16 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
   RC(allreduce_host(e, 0, 1));
   res->norm0 = std::sqrt(e->hsc[0]);
   const double thr_global = std::max(atol, o->rtol * res->norm0);
-  const double thr_local = std::max(atol, (o->rtol / std::sqrt((double)G)) * 1.0 * res->norm0);
+  // local thresholds rtol / sqrt(number of JACOBI blocks) (…-semi-local.c:330: sqrt(2)); G counts the strips (GPUs)
+  const double thr_local = std::max(atol, (o->rtol / std::sqrt((double)(G / e->npb))) * 1.0 * res->norm0);
+  // ||rhs_K - A_KK x_K|| of my Jacobi block: the strips' sums of squares added over the block's GPUs
+  auto block_local_norm = [&](double *ln) -> int {
+    RC(op_resid_sumsq(e, false, 1));
+    if (e->npb > 1) RC(e->bcomm->allreduce_sum(e->dsc + 1, 1, e->st));
+    RC(read_scalars(e, 1, 1));
+    *ln = std::sqrt(e->hsc[1]);
+    return 0;
+  };
   RC(e->comm->barrier(e->st)); // PetscBarrier before MPI_Wtime
   EventPair ev;
   CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
@@ -176,14 +195,14 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
     } else {
       if (alg == MSP_ALG_SMSM_SEMI_LOCAL) {
         // pre-minimisation x_K against the stale rhs_K (…-semi-local.c:326)
-        RC(op_resid_sumsq(e, false, 1)); RC(read_scalars(e, 1, 1)); ln = std::sqrt(e->hsc[1]);
+        RC(block_local_norm(&ln));
       } else if (alg == MSP_ALG_SMSM_LOCAL) {
         RC(op_update_rhs(e)); // …-local.c:258
       } else {
         MSP_FAIL("algorithm not handled by the synchronous driver");
       }
       RC(op_minimize(e, alg, s, mo, alpha.data(), nullptr, &lits));
-      if (alg == MSP_ALG_SMSM_LOCAL) { RC(op_resid_sumsq(e, false, 1)); RC(read_scalars(e, 1, 1)); ln = std::sqrt(e->hsc[1]); }
+      if (alg == MSP_ALG_SMSM_LOCAL) RC(block_local_norm(&ln));
       if (ln <= thr_local) sticky = 1;
       e->hsc[2] = sticky; e->hsc[3] = ln * ln;
       CK(cudaMemcpyAsync(e->dsc + 2, e->hsc + 2, 16, cudaMemcpyHostToDevice, e->st));

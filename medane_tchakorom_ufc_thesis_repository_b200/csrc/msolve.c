@@ -159,8 +159,8 @@ int main(int argc, char **argv) {
   if (npb < 1) npb = 1;
   if (nblocks < 0) nblocks = (alg == MSP_ALG_GMRES) ? 1 : 2; /* iSolve:332-338: np/npb == 2 */
   /* -npb P: P GPUs (strips) per Jacobi block, i.e. nblocks * P engines; the inner GMRES of a block is then distributed over them
-   * (SM, SMSM_GLOBAL, GMRES).  The other algorithms keep one strip per block and say so. */
-  if (npb > 1 && !(alg == MSP_ALG_SM || alg == MSP_ALG_SMSM_GLOBAL || alg == MSP_ALG_GMRES)) {
+   * (the synchronous drivers and GMRES).  The asynchronous drivers keep one strip per block and say so. */
+  if (npb > 1 && alg >= MSP_ALG_AM) { /* the asynchronous drivers */
     fprintf(stderr, "msolve: -npb %d ignored for this algorithm: a Jacobi block is one GPU (strip) here\n", npb);
     npb = 1;
   }

@@ -321,7 +321,7 @@ static int op_spmm(msp_engine *e, int kind, int s, bool diff_basis = true) {
   // basis of successive corrections (same span as the iterates, far better conditioned); the LSQR path keeps the
   // reference's raw basis [x^1 .. x^s]
   if (diff_basis) { k_diff_basis<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, s, e->ld, e->S); e->launches++; }
-  if (diff_basis && !kind_is_local(kind)) {
+  if (diff_basis && (!kind_is_local(kind) || e->npb > 1)) { // (npb > 1: the layers of the block's own neighbouring strips belong to S_K too)
     if (e->has_nb[0]) { k_diff_basis<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->H, s, e->H, e->Slo); e->launches++; }
     if (e->has_nb[1]) { k_diff_basis<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->H, s, e->H, e->Shi); e->launches++; }
   }
@@ -331,7 +331,12 @@ static int op_spmm(msp_engine *e, int kind, int s, bool diff_basis = true) {
     // gather-bound: 3.17 ms against 5 x 0.19 ms at 67 M rows); same fma chain per row, so the columns of R are unchanged
     for (int t = 0; t < s; t++) {
       SpmvArgs v = spmv_args(e, e->S + (long long)t * e->ld, e->R + (long long)t * e->ld);
-      if (local) launch_spmv_w<0, false, false, false>(e, v, 0, nullptr);
+      if (local && e->npb > 1) {
+        // A_KK of a block spread over several GPUs: stored layers of the block's own neighbouring strips, nothing from other blocks
+        v.lo = e->intra[0] ? e->Slo + (size_t)t * e->H : nullptr;
+        v.hi = e->intra[1] ? e->Shi + (size_t)t * e->H : nullptr;
+        launch_spmv_w<1, false, false, false>(e, v, 0, nullptr);
+      } else if (local) launch_spmv_w<0, false, false, false>(e, v, 0, nullptr);
       else {
         v.lo = e->has_nb[0] ? e->Slo + (size_t)t * e->H : nullptr;
         v.hi = e->has_nb[1] ? e->Shi + (size_t)t * e->H : nullptr;
@@ -343,8 +348,8 @@ static int op_spmm(msp_engine *e, int kind, int s, bool diff_basis = true) {
   SpmmArgs a{};
   a.nb = e->nb; a.W = e->W; a.H = e->H; a.s = s; a.ld = e->ld; a.lds = e->ld; a.ecol = e->ecol; a.eval = e->eval;
   a.S = e->S; a.R = e->R;
-  a.Slo = (!local && e->has_nb[0]) ? e->Slo : nullptr;
-  a.Shi = (!local && e->has_nb[1]) ? e->Shi : nullptr;
+  a.Slo = ((!local && e->has_nb[0]) || (local && e->intra[0])) ? e->Slo : nullptr;
+  a.Shi = ((!local && e->has_nb[1]) || (local && e->intra[1])) ? e->Shi : nullptr;
   const int g = grid_for(e->nb, 8);
   for (int c0 = 0; c0 < s;) {
     int nc = std::min(8, s - c0);
@@ -352,7 +357,7 @@ static int op_spmm(msp_engine *e, int kind, int s, bool diff_basis = true) {
     int use = nc >= 8 ? 8 : nc >= 5 ? 5 : nc >= 4 ? 4 : nc >= 2 ? 2 : 1;
 #define SPMM_CASE(N)                                                                                          \
   case N:                                                                                                     \
-    if (local) k_spmm_ell<0, N><<<g, MSPK_THREADS, 0, e->st>>>(a, c0);                                        \
+    if (local && e->npb == 1) k_spmm_ell<0, N><<<g, MSPK_THREADS, 0, e->st>>>(a, c0);                          \
     else k_spmm_ell<1, N><<<g, MSPK_THREADS, 0, e->st>>>(a, c0);                                              \
     break;
     switch (use) { SPMM_CASE(8) SPMM_CASE(5) SPMM_CASE(4) SPMM_CASE(2) SPMM_CASE(1) }
@@ -534,10 +539,12 @@ static int op_apply_alpha(msp_engine *e, int kind, int s, const double *alpha_ho
   CK(cudaMemcpyAsync(e->dsc + 216, e->hsc + 216, sizeof(double) * s, cudaMemcpyHostToDevice, e->st));
   k_lincomb<<<grid_for(e->nb), MSPK_THREADS, 0, e->st>>>(e->nb, s, e->ld, e->S, e->dsc + 216, e->x);
   e->launches++;
-  if (!kind_is_local(kind)) {
-    // the block's copies of the neighbours' boundaries follow x_min = S alpha too (…-semi-local.c:335-338)
+  {
+    // the block's copies of the neighbours' boundaries follow x_min = S alpha too (…-semi-local.c:335-338); the local variant
+    // only rewrites its own block (…-local.c:256-260) — which, spread over several GPUs, includes the neighbouring strips of the block
+    const bool local_kind = kind_is_local(kind);
     for (int side = 0; side < 2; side++)
-      if (e->has_nb[side]) {
+      if (local_kind ? e->intra[side] : e->has_nb[side]) {
         k_lincomb<<<grid_for(e->H), MSPK_THREADS, 0, e->st>>>(e->H, s, e->H, side ? e->Shi : e->Slo, e->dsc + 216, e->halo[side]);
         e->launches++;
       }

@@ -908,7 +908,9 @@ def test_group_abort_reports_the_failing_block(S):
 
 @pytest.mark.parametrize("alg,dims,G,npb,s,max_it", [("SMSM_GLOBAL", (48, 40, 1), 2, 2, 4, 5), ("SM", (48, 32, 1), 2, 3, 0, 20),
                                                      ("SMSM_GLOBAL", (12, 12, 16), 2, 4, 5, 5), ("SMSM_GLOBAL", (64, 48, 1), 1, 4, 5, 20),
-                                                     ("SMSM_GLOBAL", (48, 40, 1), 4, 2, 10, 5)])
+                                                     ("SMSM_GLOBAL", (48, 40, 1), 4, 2, 10, 5),
+                                                     ("SMSM_SEMI_LOCAL", (48, 40, 1), 2, 2, 4, 5), ("SMSM_LOCAL", (48, 40, 1), 2, 3, 4, 5),
+                                                     ("SMSM_LOCAL", (12, 12, 16), 2, 2, 3, 5), ("SMSM_SEMI_LOCAL", (12, 12, 16), 4, 2, 5, 5)])
 def test_jacobi_block_over_several_gpus(S, oracle, alg, dims, G, npb, s, max_it):
     """SURVEY §8 f4, the reference's -npb > 1: every Jacobi block is spread over npb strips (GPUs) and its inner GMRES runs
     distributed over them (Krylov-vector layers between the strips, MDot / norm sums over the block's communicator).  The
@@ -922,14 +924,21 @@ def test_jacobi_block_over_several_gpus(S, oracle, alg, dims, G, npb, s, max_it)
     x = grp.solution()
     tight = max_it <= 5 or alg == "SM" or G == 1
     assert np.linalg.norm(x - ref["x"]) <= (1e-8 if tight else 1e-6) * np.linalg.norm(ref["x"])
-    assert np.allclose(res[0]["hist"], ref["hist"], rtol=1e-6 if tight else 1e-2)
+    # (semi-local / local: every strip reports its block's local norm; the oracle's history keeps the worst block)
+    assert np.allclose(np.max([r["hist"] for r in res], axis=0), ref["hist"], rtol=1e-6 if tight else 1e-2)
     assert all(r["inner_its_total"] == res[0]["inner_its_total"] for r in res)  # identical control state on every strip
     grp.close()
+    # whole run: semi-local stops on sticky flags of pre-minimisation residuals (…-semi-local.c:326-333) and its count drifts on
+    # long runs even with one GPU per block (measured 32 vs 25 here at rtol 1e-6, 89 vs 73 in tools/mgpu_check.py's note): short run
+    rtol = 1e-3 if alg == "SMSM_SEMI_LOCAL" else 1e-6
     grp = S.Group(m, n, p, nblocks=G, npb=npb, s=s, max_restart=30)
-    res = grp.solve(alg, s=s, rtol=1e-6, inner=S.ksp_opts(**inner), max_outer=5000)
-    ref = oracle.solve(alg, m, n, p=p, nblocks=G, s=s, rtol=1e-6, inner=inner, max_outer=5000)
+    res = grp.solve(alg, s=s, rtol=rtol, inner=S.ksp_opts(**inner), max_outer=5000)
+    ref = oracle.solve(alg, m, n, p=p, nblocks=G, s=s, rtol=rtol, inner=inner, max_outer=5000)
     assert abs(res[0]["outer_its"] - ref["outer_its"]) <= 1, (res[0]["outer_its"], ref["outer_its"])
-    assert res[0]["final_residual"] <= 1e-6 * res[0]["norm0"] * 1.0000001
+    if alg in ("SM", "SMSM_GLOBAL"):
+        assert res[0]["final_residual"] <= rtol * res[0]["norm0"] * 1.0000001
+    else:  # the (semi-)local rule bounds the blocks' local residuals by rtol / sqrt(number of Jacobi blocks)
+        assert res[0]["last_norm"] <= rtol / np.sqrt(G) * res[0]["norm0"] * 1.0000001
     grp.close()
 
 
