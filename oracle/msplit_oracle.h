@@ -3,9 +3,13 @@
  *
  * A plain-C restatement of the reference's multisplitting solve path
  * (craftman22/medane_tchakorom_ufc_thesis_repository, C on PETSc 3.22.1 + MPICH).
- * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
- * reference legs may load this library.  The product path (libmsplit.so) never
- * links, imports or calls it.
+ * Only tests/ (and the checker scripts the tests run or that produce their
+ * evidence: tools/mgpu_check.py, tools/parity_margins.py, tools/sensitivity_*.py),
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library — always as the checker or the CPU baseline, never as the
+ * thing measured or shipped.  The product path (libmsplit.so and the package
+ * medane_tchakorom_ufc_thesis_repository_b200/) never links, imports or calls it
+ * (tests/test_cabi_and_host.py::test_product_never_imports_oracle).
  *
  * PARITY STATUS
  *   pinned   : CSR assembly (poisson2D/3D), block partition arithmetic and the
