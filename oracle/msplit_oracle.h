@@ -4,7 +4,8 @@
  * A plain-C restatement of the reference's multisplitting solve path
  * (craftman22/medane_tchakorom_ufc_thesis_repository, C on PETSc 3.22.1 + MPICH).
  * Only tests/ (and the checker scripts the tests run or that produce their
- * evidence: tools/mgpu_check.py, tools/parity_margins.py, tools/sensitivity_*.py),
+ * evidence: tools/mgpu_check.py, tools/parity_margins.py, tools/sensitivity_*.py,
+ * tools/history_1024_vs_oracle.py),
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library — always as the checker or the CPU baseline, never as the
  * thing measured or shipped.  The product path (libmsplit.so and the package
