@@ -88,7 +88,16 @@ static int ksp_from_options(const optdb *db, const char *prefix, msp_ksp_opts *o
     else { fprintf(stderr, "msolve: unknown %s %s\n", key, v); return -1; }
   }
   v = opt_find(db, KEY("ksp_type"), NULL);
-  if (v && *v && strcasecmp(v, "gmres")) { fprintf(stderr, "msolve: -%sksp_type %s is not on the device path (gmres only)\n", prefix, v); return -1; }
+  if (v && *v && !strcasecmp(v, "preonly")) {
+    /* -innerK_ksp_type preonly -innerK_pc_type lu (running_bulk_test_local:241-242): an EXACT inner solve.  There is no sparse
+     * LU on the device path; the same iterate (to rounding) comes from GMRES(64) run to rtol 1e-12 of the entry residual,
+     * capped at 20 cycles.  Anything but lu / cholesky behind preonly is refused. */
+    const char *pc = opt_find(db, KEY("pc_type"), NULL);
+    if (!pc || (strcasecmp(pc, "lu") && strcasecmp(pc, "cholesky"))) { fprintf(stderr, "msolve: -%sksp_type preonly needs -%spc_type lu (exact inner solve); other preconditioners are not on the device path\n", prefix, prefix); return -1; }
+    o->restart = MSP_MAX_RESTART; o->max_it = 20 * MSP_MAX_RESTART; o->rtol = 1e-12; o->abstol = 1e-300; o->initial_rtol = 1;
+    return 0;
+  }
+  if (v && *v && strcasecmp(v, "gmres")) { fprintf(stderr, "msolve: -%sksp_type %s is not on the device path (gmres | preonly + lu)\n", prefix, v); return -1; }
   v = opt_find(db, KEY("pc_type"), NULL);
   if (v && *v && strcasecmp(v, "none")) { fprintf(stderr, "msolve: -%spc_type %s is not supported (none only)\n", prefix, v); return -1; }
   v = opt_find(db, KEY("ksp_norm_type"), NULL);

@@ -1114,6 +1114,27 @@ def test_msolve_c_driver(S, oracle):
     b = oracle.spmv(rp, ci, va, np.ones(1024))
     _, its, _, _ = oracle.gmres(rp, ci, va, b, restart=30, rtol=1e-4, abstol=1e-100, max_it=10 ** 9, initial_rtol=1)
     assert int(re.search(r"Number of iterations of GMRES : (\d+)", out.stdout).group(1)) == its
-    # unsupported inner solver is refused loudly, not silently replaced
+    # unsupported inner solvers are refused loudly, not silently replaced
     out = subprocess.run([exe, "-alg", "SM", "-m", "16", "-n", "16", "-inner1_ksp_type", "preonly"], capture_output=True, text=True, timeout=60)
     assert out.returncode != 0 and "not on the device path" in out.stderr
+    out = subprocess.run([exe, "-alg", "SM", "-m", "16", "-n", "16", "-inner1_ksp_type", "bcgs"], capture_output=True, text=True, timeout=60)
+    assert out.returncode != 0 and "not on the device path" in out.stderr
+    # preonly + lu (the commented script line running_bulk_test_local:238-244: semi-local, 64 x 64, s = 1) = exact inner solves:
+    # same outer-iteration count as the oracle with inner solves run to 1e-12
+    cmd = [exe, "-alg", "SMSM_SEMI_LOCAL", "-npb", "1", "-m", "64", "-n", "64", "-s", "1", "-rtol", "1e-3"]
+    for k in (1, 2):
+        cmd += [f"-inner{k}_ksp_type", "preonly", f"-inner{k}_pc_type", "lu"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    ref = oracle.solve("SMSM_SEMI_LOCAL", 64, 64, nblocks=2, s=1, rtol=1e-3, inner=dict(restart=64, max_it=1280, rtol=1e-12, abstol=1e-300))
+    m = re.search(r"\[ Block rank 0 \] Total number of iterations \(outer_iterations \* s\) = (\d+) \* 1", out.stdout)
+    assert m and abs(int(m.group(1)) - ref["outer_its"]) <= 1, (out.stdout, ref["outer_its"])
+    # ... and plain block-Jacobi with exact block solves (MSM): the sweep count of the oracle with inner solves run to 1e-12
+    out = subprocess.run([exe, "-alg", "SM", "-m", "32", "-n", "32", "-rtol", "1e-6", "-inner_ksp_type", "preonly", "-inner_pc_type", "lu"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    ref = oracle.solve("SM", 32, 32, nblocks=2, s=0, rtol=1e-6, inner=dict(restart=64, max_it=1280, rtol=1e-12, abstol=1e-300))
+    m = re.search(r"\[ Block rank 0 \] Total number of iterations \(outer_iterations\) = (\d+)", out.stdout)
+    assert m and abs(int(m.group(1)) - ref["outer_its"]) <= 1, (out.stdout, ref["outer_its"])
+    fr = float(re.search(r"Final residual norm 2 = ([0-9.e+-]+)", out.stdout).group(1))
+    assert fr <= 1e-6 * ref["norm0"] * 1.000001
