@@ -290,7 +290,8 @@ def time_to_rtol_leg(args, world, npb=1):
     eng.close()
     rel = res["final_residual"] / res["norm0"]
     return {"reached": bool(rel <= RTOL * 1.000001), "seconds": t_dev, "unit": "s", "outer_iterations": int(res["outer_its"]),
-            "inner_iterations_per_block": int(res["inner_its_total"]), "true_rel_residual": float(rel),
+            "inner_iterations_per_block": int(res["inner_its_total"]),
+            "ms_per_arnoldi_step": float(t_dev * 1e3 / max(1, int(res["inner_its_total"]))), "true_rel_residual": float(rel),
             "stopping_quantity_rel": float(res["last_norm"] / res["norm0"]),
             "stop_reason": {0: "converged", 1: "max_outer", 2: "max_seconds"}[res["stop_reason"]],
             "error_norm": float(res["error"]), "gpu_launches": launches, "clocks": clocks,
