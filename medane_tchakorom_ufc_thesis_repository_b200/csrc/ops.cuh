@@ -76,6 +76,7 @@ static const double *intra_hi(const msp_engine *e) { return e->intra[1] ? e->win
 static int op_inner_solve_dist(msp_engine *e, const msp_ksp_opts *o, bool publish, int *its_out, int *reason_out, double *rnorm_out, bool defer) {
   if (o->restart < 1 || o->restart > e->prob.max_restart) MSP_FAIL("restart exceeds max_restart of the engine");
   if (o->mgs) MSP_FAIL("modified Gram-Schmidt is not available for a Jacobi block spread over several GPUs (npb > 1)");
+  if (e->bcomm->nranks != e->npb) MSP_FAIL("npb > 1 but the block's communicator is not set up: create the engines through msp_group_create or call msp_comm_init");
   defer = defer && !its_out && !reason_out && !rnorm_out && o->max_it <= 4 * o->restart;
   const bool guess_zero = !o->guess_nonzero;
   double *bnorm_sq = nullptr;

@@ -1052,6 +1052,12 @@ def test_errors(S):
     with pytest.raises(S.MsplitError):
         S.Engine(10, 10, nblocks=3)  # grid lines not divisible by the block count
     with pytest.raises(S.MsplitError):
+        S.Engine(12, 12, nblocks=4, npb=3)  # strips not divisible into blocks of npb
+    e = S.Engine(12, 12, block=0, nblocks=2, npb=2)  # a strip of a two-GPU block, but nobody wired the block's communicator
+    with pytest.raises(S.MsplitError, match="communicator"):
+        e.inner_solver(S.ksp_opts(restart=5, max_it=5))
+    e.close()
+    with pytest.raises(S.MsplitError):
         S.Engine(8, 8, max_restart=100)
     g = S.Group(16, 16, nblocks=2, s=2)
     with pytest.raises(S.MsplitError):
