@@ -169,6 +169,12 @@ int msp_halo_size(const msp_engine *e); /* one grid line (2-D) / plane (3-D) */
  * 0 = slot-major ELL (values + indices, 12*width + 16 bytes per row); *width = diagonals / slots.
  * Environment: MSPLIT_NO_CDIA=1 keeps the plain DIA view, MSPLIT_NO_DIA=1 the ELL view. */
 int msp_spmv_format(const msp_engine *e, int *width);
+/* 1 when this engine runs each GMRES restart cycle (KSPGMRESCycle: the loop inside inner_solver utils.c:950-970) as ONE
+ * persistent cooperative kernel with grid barriers instead of one kernel per phase — chosen for small blocks, where the
+ * phases are launch-bound; the iterates are bit-identical either way.  Needs the coded-DIA stencil view, one GPU per
+ * Jacobi block, classical Gram-Schmidt without refinement.  Environment: MSPLIT_COOP=0 never, MSPLIT_COOP=1 for every
+ * eligible block, default: blocks of at most MSPLIT_COOP_MAX_ROWS rows. */
+int msp_persistent_cycles(const msp_engine *e);
 int64_t msp_mat_nnz(msp_engine *e, int which);
 int msp_get_csr(msp_engine *e, int which, int32_t *rowptr, int32_t *colidx, double *val);
 int msp_set_b(msp_engine *e, const double *b);

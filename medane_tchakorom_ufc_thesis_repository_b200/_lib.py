@@ -75,7 +75,7 @@ class Result(C.Structure):
 EXPORTS = [
     "msp_version", "msp_last_error", "msp_device_count", "msp_poisson2d_nnz", "msp_poisson3d_nnz",
     "msp_assemble_poisson2d", "msp_assemble_poisson2d_complete", "msp_assemble_poisson3d", "msp_dimension_related",
-    "msp_create", "msp_destroy", "msp_rows", "msp_halo_size", "msp_spmv_format", "msp_mat_nnz", "msp_get_csr", "msp_set_b", "msp_get_b",
+    "msp_create", "msp_destroy", "msp_rows", "msp_halo_size", "msp_spmv_format", "msp_persistent_cycles", "msp_mat_nnz", "msp_get_csr", "msp_set_b", "msp_get_b",
     "msp_set_x", "msp_get_x", "msp_set_halo", "msp_get_halo", "msp_get_rhs", "msp_update_local_rhs", "msp_inner_solve",
     "msp_local_residual_norm", "msp_block_residual_norm", "msp_error_norm_sq", "msp_push_iterate", "msp_spmm_AS",
     "msp_minimize_local_qr", "msp_apply_alpha", "msp_tsqr_combine", "msp_op_spmv", "msp_op_mdot", "msp_op_maxpy",
@@ -116,6 +116,7 @@ def lib() -> C.CDLL:
     L.msp_rows.argtypes = [vp]
     L.msp_halo_size.argtypes = [vp]
     L.msp_spmv_format.argtypes = [vp, C.POINTER(C.c_int)]
+    L.msp_persistent_cycles.argtypes = [vp]
     L.msp_mat_nnz.restype = C.c_int64
     L.msp_mat_nnz.argtypes = [vp, C.c_int]
     L.msp_get_csr.argtypes = [vp, C.c_int, i32p, i32p, f64p]

@@ -66,6 +66,10 @@ int msp_spmv_format(const msp_engine *e, int *width) {
   if (width) *width = (e->dval || e->dmask) ? e->dia.nd : e->W;
   return e->dmask ? 2 : e->dval ? 1 : 0;
 }
+int msp_persistent_cycles(const msp_engine *e) {
+  if (!e) return -1;
+  return (e->coop_mode == 1 || (e->coop_mode == 2 && e->nb <= e->coop_max_rows)) ? 1 : 0;
+}
 int msp_halo_size(const msp_engine *e) { return e ? e->H : -1; }
 
 static int sub_extract(msp_engine *e, int which, int32_t *orp_h, int32_t *oci_h, double *ova_h, int64_t *nnz_out) {
@@ -465,6 +469,12 @@ int msp_group_create(const msp_problem *prob, int nblocks, const int *devices, m
     int rc = engine_create(&p, devices ? devices[k] : 0, &e);
     if (rc) { for (auto *x : g->eng) engine_free(x); for (auto *b : g->bsh) delete b; delete g->sh; delete g; return rc; }
     g->eng.push_back(e);
+  }
+  // the block threads run their inner solves at the same time: engines on one GPU share it (persistent cycle kernel: cycle_coop.cuh)
+  for (auto *e : g->eng) {
+    e->coop_share = 0;
+    for (auto *o : g->eng) e->coop_share += (o->device == e->device) ? 1 : 0;
+    coop_configure(e);
   }
   int rc = group_wire(g);
   if (rc) { for (auto *x : g->eng) engine_free(x); for (auto *b : g->bsh) delete b; delete g->sh; delete g; return rc; }

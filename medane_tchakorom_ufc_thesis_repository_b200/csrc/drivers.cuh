@@ -230,6 +230,7 @@ static int engine_solve_sync(msp_engine *e, const msp_solve_opts *o, msp_result 
     CK(cudaMemcpy(&tot, reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, its_total), sizeof(long long), cudaMemcpyDeviceToHost));
     res->inner_its_total = tot;
   }
+  RC(coop_check(e)); // the deferred inner solves read nothing back: a barrier timeout of the persistent kernel surfaces here
   e->prof_collect(res);
   e->prof = false;
   // closing exchange + true residual + error (comm_sync_send_and_receive_final comm.c:199, utils.c:575, :1045)

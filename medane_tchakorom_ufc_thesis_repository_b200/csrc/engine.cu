@@ -2,6 +2,7 @@
 // See include/msplit.h for the reference function each entry point replaces.
 #include "../../include/msplit.h"
 #include "kernels.cuh"
+#include "cycle_coop.cuh"
 
 #include <cub/device/device_scan.cuh>
 #include <dlfcn.h>
@@ -49,13 +50,7 @@ struct StageRange {
 };
 
 static int g_num_sms = 148;
-static inline int grid_for(long long work_items, int per_sm = 8) {
-  long long need = (work_items + MSPK_THREADS - 1) / MSPK_THREADS;
-  long long cap = (long long)g_num_sms * per_sm;
-  if (cap > MSPK_MAX_PART - 1) cap = (MSPK_MAX_PART - 1) / g_num_sms * g_num_sms;
-  if (need < 1) need = 1;
-  return (int)std::min(need, cap);
-}
+static inline int grid_for(long long work_items, int per_sm = 8) { return msp_grid_for(work_items, per_sm, g_num_sms); }
 
 #include "comm.cuh"
 
@@ -187,6 +182,13 @@ struct msp_engine {
   struct CycleGraph { cudaGraphExec_t exec; int launches; };
   std::map<CycleKey, CycleGraph> cycle_graphs;
   bool use_graphs = true;
+  // persistent cooperative restart-cycle kernel (cycle_coop.cuh) for small blocks: 0 = never, 1 = whenever eligible,
+  // 2 = when eligible and nb <= coop_max_rows
+  int coop_mode = 0; long long coop_max_rows = 0; int coop_grid = 0;
+  int coop_per_sm = 1;  // resident blocks per SM the cycle kernel allows (2)
+  int coop_share = 1;   // engines expected to run their cycles at the same time on this GPU (all blocks in one process)
+  unsigned int *coop_bar = nullptr; // [0] arrival counter, [1] sticky abort flag, [2] count at the end of the previous launch
+  int coop_vg_prologue = 0;
   // deterministic turn taking for the emulated asynchronous schedule
   struct msp_group *grp = nullptr;
 };
@@ -324,32 +326,26 @@ static SpmvArgs spmv_args(msp_engine *e, const double *x, double *y) {
   return a;
 }
 
+// vectors per y-group of VecMDot (measured at 67 M rows: 8 -> 6.6-6.9 TB/s for nv > 8, 24 -> 7.0-7.3); MSPLIT_MDOT_GROUP is a debug switch
+static int mdot_gmax() {
+  static const int gmax = getenv("MSPLIT_MDOT_GROUP") ? std::min(24, std::max(1, atoi(getenv("MSPLIT_MDOT_GROUP")))) : 24;
+  return gmax;
+}
 static void launch_mdot(msp_engine *e, int nv, const double *V, long long ldv, const double *w, double *h, double sign, int guard_it,
                         int guard_refine, const double *inv = nullptr) {
   MdotArgs a{};
   a.nb = e->nb; a.nv = nv; a.ld = ldv; a.V = V; a.w = w; a.h = h; a.sign = sign; a.ctl = e->ctl; a.inv = inv;
   a.guard_it = guard_it; a.guard_refine = guard_refine;
-  static const int gmax = getenv("MSPLIT_MDOT_GROUP") ? std::min(24, std::max(1, atoi(getenv("MSPLIT_MDOT_GROUP")))) : 24; // vectors per y-group (measured at 67 M rows: 8 -> 6.6-6.9 TB/s for nv > 8, 24 -> 7.0-7.3)
-  int ngroups = (nv + gmax - 1) / gmax;
-  a.per_group = (nv + ngroups - 1) / ngroups;
-  ngroups = (nv + a.per_group - 1) / a.per_group;
-  int per_sm = std::max(1, 8 / ngroups);
+  const MdotGeom gm = mdot_geometry(e->nb, nv, mdot_gmax(), g_num_sms);
+  a.per_group = gm.per_group;
   e->prof_begin(1, 8.0 * e->nb * (nv + 1));
-  if (a.per_group > 16) {
-    dim3 grid(grid_for((long long)e->nb / 2, 1), ngroups);
-    k_mdot<24, 1><<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws);
-  } else if (a.per_group > 8) {
-    dim3 grid(grid_for((long long)e->nb / 2, std::min(per_sm, 2)), ngroups);
-    k_mdot<16, 1><<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws);
-  } else if (a.per_group <= 2) {
-    dim3 grid(grid_for((long long)e->nb / 16, per_sm), ngroups);
-    k_mdot<2, 8><<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws);
-  } else if (a.per_group <= 4) {
-    dim3 grid(grid_for((long long)e->nb / 8, per_sm), ngroups);
-    k_mdot<4, 4><<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws);
-  } else {
-    dim3 grid(grid_for((long long)e->nb / 4, per_sm), ngroups);
-    k_mdot<8, 2><<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws);
+  const dim3 grid(gm.gx, gm.ngroups);
+  switch (gm.variant) {
+    case 24: k_mdot<24, 1><<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws); break;
+    case 16: k_mdot<16, 1><<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws); break;
+    case 2: k_mdot<2, 8><<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws); break;
+    case 4: k_mdot<4, 4><<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws); break;
+    default: k_mdot<8, 2><<<grid, MSPK_THREADS, 0, e->st>>>(a, e->ws); break;
   }
   e->prof_end();
   e->launches++;
@@ -368,6 +364,84 @@ static void launch_maxpy(msp_engine *e, int nv, const double *V, long long ldv, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// persistent cooperative restart-cycle kernel (cycle_coop.cuh)
+// ------------------------------------------------------------------------------------------------
+// MSPLIT_COOP=0 never, =1 whenever the block is eligible; default: eligible blocks of at most MSPLIT_COOP_MAX_ROWS rows.
+// The default bound is where the one-kernel-per-phase path stops being launch-bound (measured).
+// Defaults from tools/coop_probe.py on one B200 (profiles/r02_coop_probe.txt): alone on its GPU an engine runs the cycle
+// kernel with two blocks per SM and gains up to ~0.8 M rows per block; two engines sharing a GPU take one block per SM each
+// (so that both cycles are resident side by side) and gain up to ~0.4 M rows; more than two engines per GPU keep one kernel
+// per phase (their cooperative launches could only run one after the other).
+#ifndef MSPK_COOP_DEFAULT_MAX_ROWS
+#define MSPK_COOP_DEFAULT_MAX_ROWS 786432LL
+#endif
+static void coop_configure(msp_engine *e) {
+  if (!e->coop_mode) return;
+  const int share = std::max(1, e->coop_share);
+  int want = getenv("MSPLIT_COOP_CTAS_PER_SM") ? atoi(getenv("MSPLIT_COOP_CTAS_PER_SM")) : e->coop_per_sm / share;
+  want = std::max(1, std::min(want, e->coop_per_sm));
+  e->coop_grid = g_num_sms * want;
+  if (getenv("MSPLIT_COOP_MAX_ROWS")) e->coop_max_rows = atoll(getenv("MSPLIT_COOP_MAX_ROWS"));
+  else e->coop_max_rows = (share > e->coop_per_sm) ? 0 : MSPK_COOP_DEFAULT_MAX_ROWS / share;
+}
+static int coop_setup(msp_engine *e) {
+  e->coop_mode = 0;
+  const char *env = getenv("MSPLIT_COOP");
+  if (env && atoi(env) == 0) return 0;
+  // eligible: coded DIA of stencil shape (the hot SpMV), one GPU per Jacobi block, the default MDot grouping
+  if (!e->dmask || !e->dia_stencil || e->npb != 1 || mdot_gmax() != 24) return 0;
+  if (e->dia.nd != 5 && e->dia.nd != 7) return 0;
+  int coop = 0;
+  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device) != cudaSuccess || !coop) { cudaGetLastError(); return 0; }
+  int per_sm = 0;
+  const cudaError_t er = (e->dia.nd == 5) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gmres_cycle_coop<5>, MSPK_THREADS, 0)
+                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gmres_cycle_coop<7>, MSPK_THREADS, 0);
+  if (er != cudaSuccess || per_sm < 1) { cudaGetLastError(); return 0; }
+  e->coop_per_sm = std::min(per_sm, 2);
+  if (cudaMalloc(&e->coop_bar, 4 * sizeof(unsigned int)) != cudaSuccess) MSP_FAIL("out of device memory (barrier word)");
+  CK(cudaMemsetAsync(e->coop_bar, 0, 4 * sizeof(unsigned int), e->st));
+  // the virtual grid of the prologue SpMV of the one-kernel-per-phase path (launch_spmv_w<0, true, false, true>)
+  const long long quads = ((long long)e->nb + 3) / 4;
+  e->coop_vg_prologue = (e->dia.nd == 5) ? grid_for(quads, resident_blocks_per_sm(k_spmv_cdia_stencil<5, 0, true, false, true>))
+                                         : grid_for(quads, resident_blocks_per_sm(k_spmv_cdia_stencil<7, 0, true, false, true>));
+  e->coop_mode = (env && atoi(env) == 1) ? 1 : 2;
+  coop_configure(e);
+  return 0;
+}
+static bool coop_eligible(const msp_engine *e, const msp_ksp_opts *o, int cgs_refine, bool from_rhs) {
+  if (!e->coop_mode || e->prof || from_rhs || o->mgs || cgs_refine) return false;
+  if (e->coop_mode == 2 && e->nb > e->coop_max_rows) return false;
+  return ((((uintptr_t)e->x | (uintptr_t)e->V | (uintptr_t)e->rhs) & 31) == 0);
+}
+// one restart cycle of at most nsteps steps as ONE launch
+static int launch_cycle_coop(msp_engine *e, int nsteps, double *peer_lo, double *peer_hi) {
+  CycleCoopArgs a{};
+  a.sp = spmv_args(e, e->x, e->V);
+  a.nb = e->nb; a.H = e->H; a.nsteps = nsteps; a.num_sms = g_num_sms; a.mdot_gmax = mdot_gmax();
+  a.vg_prologue = e->coop_vg_prologue;
+  a.vg_maxpy = grid_for((long long)e->nb / 4, 8);
+  a.ld = e->ld; a.V = e->V; a.x = e->x; a.rhs = e->rhs; a.ctl = e->ctl; a.peer_lo = peer_lo; a.peer_hi = peer_hi;
+  a.ws = e->ws; a.bar = e->coop_bar;
+  void *args[] = {&a};
+  const void *fn = (e->dia.nd == 5) ? (const void *)k_gmres_cycle_coop<5> : (const void *)k_gmres_cycle_coop<7>;
+  CK(cudaLaunchCooperativeKernel(fn, dim3(e->coop_grid), dim3(MSPK_THREADS), args, 0, e->st));
+  e->launches++;
+  return 0;
+}
+// a barrier of the persistent kernel timed out (its blocks were not co-resident, or a block died): never silent
+static int coop_check(msp_engine *e) {
+  if (!e->coop_mode) return 0;
+  unsigned int flag = 0;
+  CK(cudaMemcpyAsync(&flag, e->coop_bar + 1, sizeof(flag), cudaMemcpyDeviceToHost, e->st));
+  CK(cudaStreamSynchronize(e->st));
+  if (flag) {
+    e->coop_mode = 0; // fall back to one kernel per phase for whatever the caller does next
+    MSP_FAIL("the persistent restart-cycle kernel timed out in a grid barrier (MSPLIT_COOP=0 disables it)");
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // create / destroy
 // ------------------------------------------------------------------------------------------------
 static int engine_free(msp_engine *e) {
@@ -378,7 +452,7 @@ static int engine_free(msp_engine *e) {
   for (int J = 0; J < MSP_MAX_BLOCKS; J++)
     if (e->peer_any[J].base && e->peer_any_ipc[J]) cudaIpcCloseMemHandle(e->peer_any[J].base);
   void *ptrs[] = {e->rp, e->ci, e->va, e->ecol, e->eval, e->dval, e->dmask, e->brow, e->b, e->rhs, e->x, e->halo[0], e->halo[1], e->V, e->Wb[0],
-                  e->Wb[1], e->S, e->Slo, e->Shi, e->R, e->ctl, e->ws.partial, e->ws.counter, e->dsc, e->dfac, e->gram_partial, e->win.base, e->cd, e->aint, e->dec};
+                  e->Wb[1], e->S, e->Slo, e->Shi, e->R, e->ctl, e->ws.partial, e->ws.counter, e->dsc, e->dfac, e->gram_partial, e->win.base, e->cd, e->aint, e->dec, e->coop_bar};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (e->st_copy) { cudaStreamSynchronize(e->st_copy); cudaStreamDestroy(e->st_copy); }
   if (e->ev_copy) cudaEventDestroy(e->ev_copy);
@@ -581,6 +655,7 @@ static int engine_create(const msp_problem *p, int device, msp_engine **out) {
   e->comm = new SelfComm(); e->own_comm = true;
   e->bcomm = e->comm; e->own_bcomm = false; // one GPU per block until a group / msp_comm_init wires the block's ranks
   e->use_graphs = getenv("MSPLIT_NO_GRAPHS") == nullptr;
+  if (coop_setup(e)) return fail(1);
   if (op_compute_rhs_ones(e)) return fail(1);
   if (cudaStreamSynchronize(e->st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { g_err = "setup kernels failed"; return fail(1); }
   e->launches = 0;

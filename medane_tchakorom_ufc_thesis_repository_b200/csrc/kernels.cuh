@@ -20,6 +20,33 @@
 #define MSPK_CDIA_MINB7 4
 #endif
 
+// grid of a grid-stride kernel: enough blocks for the work, at most `per_sm` per SM and fewer than MSPK_MAX_PART (one
+// reduction partial per block).  Host and device share it: the persistent restart-cycle kernel (cycle_coop.cuh) forms its
+// reduction partials over the SAME virtual grids as the one-kernel-per-phase path, which is what makes the two bit-identical.
+__host__ __device__ inline int msp_grid_for(long long work_items, int per_sm, int num_sms) {
+  long long need = (work_items + MSPK_THREADS - 1) / MSPK_THREADS;
+  long long cap = (long long)num_sms * per_sm;
+  if (cap > MSPK_MAX_PART - 1) cap = (MSPK_MAX_PART - 1) / num_sms * num_sms;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+// launch geometry of VecMDot over nv vectors: y-groups of <= gmax vectors, kernel variant and x-grid per group size
+struct MdotGeom { int per_group, ngroups, gx, variant; }; // variant: 24 / 16 / 8 / 4 / 2 = NVMAX of k_mdot
+__host__ __device__ inline MdotGeom mdot_geometry(int nb, int nv, int gmax, int num_sms) {
+  MdotGeom g;
+  g.ngroups = (nv + gmax - 1) / gmax;
+  g.per_group = (nv + g.ngroups - 1) / g.ngroups;
+  g.ngroups = (nv + g.per_group - 1) / g.per_group;
+  int per_sm = 8 / g.ngroups;
+  if (per_sm < 1) per_sm = 1;
+  if (g.per_group > 16) { g.variant = 24; g.gx = msp_grid_for((long long)nb / 2, 1, num_sms); }
+  else if (g.per_group > 8) { g.variant = 16; g.gx = msp_grid_for((long long)nb / 2, per_sm < 2 ? per_sm : 2, num_sms); }
+  else if (g.per_group <= 2) { g.variant = 2; g.gx = msp_grid_for((long long)nb / 16, per_sm, num_sms); }
+  else if (g.per_group <= 4) { g.variant = 4; g.gx = msp_grid_for((long long)nb / 8, per_sm, num_sms); }
+  else { g.variant = 8; g.gx = msp_grid_for((long long)nb / 4, per_sm, num_sms); }
+  return g;
+}
+
 // ------------------------------------------------------------------------------------------------
 // device-resident GMRES control block (KSP_GMRES of PETSc: HH, cc/ss rotations, GRS, convergence
 // context).  Kernels read `active`/`it` to turn into no-ops once the cycle has ended, so that a whole
@@ -395,10 +422,12 @@ struct SpmvArgs {
   int guard_it;         // run only if ctl->active && ctl->it == guard_it  (-1: always)
 };
 
-template <int MODE>
+// COH: the vector being read was written earlier in the SAME kernel by other thread blocks (persistent restart-cycle
+// kernel): read it through L2 (ld.cg) instead of the non-coherent path; the value loaded is the same double.
+template <int MODE, bool COH = false>
 __device__ __forceinline__ double gather_x(const SpmvArgs &a, int c, double inv, bool scale) {
   if ((unsigned)c < (unsigned)a.nb) {
-    double v = __ldg(a.x + c);
+    double v = COH ? __ldcg(a.x + c) : __ldg(a.x + c);
     return scale ? v * inv : v;
   }
   if (MODE == 0) return 0.0;
@@ -515,6 +544,9 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_spmv_dia(SpmvArgs a, ReduceWs 
 __device__ __forceinline__ void ld4_cached(const double *p, double (&v)[4]) {
   asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
+__device__ __forceinline__ void ld4_l2(const double *p, double (&v)[4]) { // coherent at L2 (see gather_x, COH)
+  asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void st4(double *p, const double (&v)[4]) {
   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
@@ -614,7 +646,7 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_spmv_cdia(SpmvArgs a, ReduceWs
 //     otherwise addresses are clamped into the block and the quads whose columns fall outside it (or into a
 //     neighbour's boundary layer) are patched through gather_x;
 //   * all presence bytes of the warp full (no domain face among its 128 rows): plain fma chain, no selects.
-template <int ND, int MODE, bool RESID, bool SCALE, bool NORM, bool INTERIOR>
+template <int ND, int MODE, bool RESID, bool SCALE, bool NORM, bool INTERIOR, bool COH = false>
 __device__ __forceinline__ void cdia_stencil_trip(const SpmvArgs &a, long long q, int nvalid, int lane, double inv, int last4, double &nrm) {
   constexpr int C = ND / 2;   // main diagonal; C - 1 / C + 1 are the -1 / +1 neighbours
   constexpr int NF = ND - 3;  // far diagonals
@@ -624,18 +656,20 @@ __device__ __forceinline__ void cdia_stencil_trip(const SpmvArgs &a, long long q
   double own[4], far[NF][4], bv[4], xm1, xp4;
   int cf[NF];
   const int rc = INTERIOR ? (int)r : ((r < last4) ? (int)r : last4);
-  ld4_cached(a.x + rc, own);
+  if (COH) ld4_l2(a.x + rc, own); else ld4_cached(a.x + rc, own);
 #pragma unroll
   for (int f = 0; f < NF; f++) {
     cf[f] = (int)r + a.dia.off[(f < C - 1) ? f : f + 3];
-    ld4_cached(a.x + (INTERIOR ? cf[f] : min(max(cf[f], 0), last4)), far[f]);
+    if (COH) ld4_l2(a.x + (INTERIOR ? cf[f] : min(max(cf[f], 0), last4)), far[f]);
+    else ld4_cached(a.x + (INTERIOR ? cf[f] : min(max(cf[f], 0), last4)), far[f]);
   }
   if (RESID) ld4_cached(a.b + rc, bv);
   const unsigned m = (INTERIOR || nvalid) ? __ldg(reinterpret_cast<const unsigned *>(a.dmask) + q) : 0u;
   double edge = 0.0;
   if (INTERIOR) { // one predicated load (never a branch: it must leave with the others, not after the first use of `own`)
     const double *pe = a.x + r + ((lane == 0) ? -1 : 4);
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.f64 %0, [%1];\n\t}" : "+d"(edge) : "l"(pe), "r"((int)(lane == 0 || lane == 31)));
+    if (COH) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.cg.f64 %0, [%1];\n\t}" : "+d"(edge) : "l"(pe), "r"((int)(lane == 0 || lane == 31)) : "memory");
+    else asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.f64 %0, [%1];\n\t}" : "+d"(edge) : "l"(pe), "r"((int)(lane == 0 || lane == 31)));
   }
   // ---- own quad and its two outer neighbours
   if (SCALE) {
@@ -645,7 +679,7 @@ __device__ __forceinline__ void cdia_stencil_trip(const SpmvArgs &a, long long q
   }
   if (!INTERIOR && nvalid != 4) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) own[i] = (i < nvalid) ? gather_x<MODE>(a, (int)r + i, inv, SCALE) : 0.0;
+    for (int i = 0; i < 4; i++) own[i] = (i < nvalid) ? gather_x<MODE, COH>(a, (int)r + i, inv, SCALE) : 0.0;
   }
   {
     const double up = __shfl_up_sync(0xffffffffu, own[3], 1), dn = __shfl_down_sync(0xffffffffu, own[0], 1);
@@ -653,9 +687,9 @@ __device__ __forceinline__ void cdia_stencil_trip(const SpmvArgs &a, long long q
     xp4 = (INTERIOR && lane == 31) ? edge : dn;
   }
   if (!INTERIOR) {
-    if (nvalid && lane == 0) xm1 = gather_x<MODE>(a, (int)r - 1, inv, SCALE);
+    if (nvalid && lane == 0) xm1 = gather_x<MODE, COH>(a, (int)r - 1, inv, SCALE);
     if (nvalid == 4) {
-      if (lane == 31 || r + 4 >= a.nb) xp4 = gather_x<MODE>(a, (int)r + 4, inv, SCALE); // the next lane holds no row
+      if (lane == 31 || r + 4 >= a.nb) xp4 = gather_x<MODE, COH>(a, (int)r + 4, inv, SCALE); // the next lane holds no row
     } else xp4 = 0.0; // only row r + 3 would use it
   }
   // ---- far diagonals
@@ -667,7 +701,7 @@ __device__ __forceinline__ void cdia_stencil_trip(const SpmvArgs &a, long long q
     }
     if (!INTERIOR && (nvalid != 4 || cf[f] < 0 || cf[f] + 3 >= a.nb)) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) far[f][i] = (i < nvalid) ? gather_x<MODE>(a, cf[f] + i, inv, SCALE) : 0.0;
+      for (int i = 0; i < 4; i++) far[f][i] = (i < nvalid) ? gather_x<MODE, COH>(a, cf[f] + i, inv, SCALE) : 0.0;
     }
   }
   // ---- fma chains in diagonal (= sorted column) order
@@ -751,6 +785,17 @@ struct MdotArgs {
   const GmresCtl *ctl;
   int guard_it, guard_refine; // guard_refine: run only if ctl->refine (second CGS pass)
 };
+
+// one warp sums the block partials of one vector: lane-strided over the blocks in index order, then the shuffle tree
+__device__ __forceinline__ double mdot_sum_partials(const double *row, int nblocks, int lane) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int i = lane;
+  for (; i + 96 < nblocks; i += 128) {
+    s0 += __ldcg(row + i); s1 += __ldcg(row + i + 32); s2 += __ldcg(row + i + 64); s3 += __ldcg(row + i + 96);
+  }
+  for (; i < nblocks; i += 32) s0 += __ldcg(row + i);
+  return warp_sum((s0 + s1) + (s2 + s3));
+}
 
 template <int NVMAX, int U>
 __global__ void __launch_bounds__(MSPK_THREADS, NVMAX > 16 ? 1 : 2) k_mdot(MdotArgs a, ReduceWs ws) {
@@ -839,14 +884,7 @@ __global__ void __launch_bounds__(MSPK_THREADS, NVMAX > 16 ? 1 : 2) k_mdot(MdotA
     // block barriers each: ~1.2 us per vector, 11 % of a 170 us launch at 8.4 M rows and 20 vectors.)
     __threadfence();
     for (int v = wid; v < nv; v += MSPK_THREADS / 32) {
-      const double *row = ws.partial + (64 + g * NVMAX + v) * (long long)MSPK_MAX_PART;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int i = lane;
-      for (; i + 96 < (int)gridDim.x; i += 128) {
-        s0 += __ldcg(row + i); s1 += __ldcg(row + i + 32); s2 += __ldcg(row + i + 64); s3 += __ldcg(row + i + 96);
-      }
-      for (; i < (int)gridDim.x; i += 32) s0 += __ldcg(row + i);
-      const double tot = warp_sum((s0 + s1) + (s2 + s3));
+      const double tot = mdot_sum_partials(ws.partial + (64 + g * NVMAX + v) * (long long)MSPK_MAX_PART, (int)gridDim.x, lane);
       // <w, v_j> = inv_j <w, vtilde_j>: the scale of the un-normalised basis vector is applied to the reduced value
       if (lane == 0) a.h[v0 + v] = a.sign * (a.inv ? tot * a.inv[v0 + v] : tot);
     }
@@ -972,8 +1010,7 @@ __global__ void __launch_bounds__(MSPK_THREADS) k_maxpy_norm(MaxpyArgs a, Reduce
 //     new iterate is stored straight into the neighbours' receive windows (P2P stores over NVLink when
 //     the neighbour lives on another GPU) — replaces comm_sync_send_and_receive comm.c:126-141.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_build_soln_coef(GmresCtl *c) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ inline void ctl_build_soln(GmresCtl *c) {
   const int ld = MSPK_MAXK + 2;
   const int k1 = c->it - 1;
   if (k1 < 0) return;
@@ -989,6 +1026,10 @@ __global__ void k_build_soln_coef(GmresCtl *c) {
     c->nrs[k] = t / c->hh[(size_t)k * ld + k];
   }
   if (bad) { c->reason = -5; c->it = 0; /* no update */ }
+}
+__global__ void k_build_soln_coef(GmresCtl *c) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ctl_build_soln(c);
 }
 
 struct UpdateXArgs {

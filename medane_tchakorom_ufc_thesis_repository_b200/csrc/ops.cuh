@@ -243,7 +243,11 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
       CK(cudaMemcpyAsync(e->hsc + 32, reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, its), 16, cudaMemcpyDeviceToHost, e->st));
       return 0;
     };
-    if (e->use_graphs && !e->prof) {
+    if (coop_eligible(e, o, cgs_refine, from_rhs)) {
+      // small block: the whole cycle is one persistent cooperative kernel (cycle_coop.cuh), bit-identical to the launches below
+      RC(launch_cycle_coop(e, nsteps, peer_lo, peer_hi));
+      CK(cudaMemcpyAsync(e->hsc + 32, reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, its), 16, cudaMemcpyDeviceToHost, e->st));
+    } else if (e->use_graphs && !e->prof) {
       const msp_engine::CycleKey key(nsteps, cgs_refine + 4 * (o->mgs ? 1 : 0), from_rhs ? 1 : 0, (const void *)e->V, (const void *)peer_lo, (const void *)peer_hi);
       auto itg = e->cycle_graphs.find(key);
       if (itg == e->cycle_graphs.end()) {
@@ -275,6 +279,7 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
     CK(cudaStreamSynchronize(e->st));
     memcpy(&hc, e->hsc + 32, 16);
     itcount += hc.it;
+    if (hc.reason == MSPK_COOP_REASON_ABORT) { RC(coop_check(e)); MSP_FAIL("the persistent restart-cycle kernel gave up"); }
     if (hc.reason) break;
     if (itcount >= o->max_it) { hc.reason = MSP_DIVERGED_ITS; break; }
     if (hc.it == 0) { hc.reason = MSP_DIVERGED_BREAKDOWN; break; } // a cycle that made no step can never end the loop

@@ -93,6 +93,10 @@ class Engine:
         kind = _lib.lib().msp_spmv_format(self.h, C.byref(w))
         return {2: "cdia", 1: "dia"}.get(kind, "ell"), w.value
 
+    def persistent_cycles(self):
+        """True when each GMRES restart cycle of this block runs as one persistent cooperative kernel (small blocks)."""
+        return _lib.lib().msp_persistent_cycles(self.h) == 1
+
     @staticmethod
     def spmv_bytes_per_row(fmt, width):
         """Bytes per row the SpMV of that storage streams (matrix + x once + y once)."""

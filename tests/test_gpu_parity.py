@@ -653,6 +653,87 @@ def test_run_to_run_bitwise_reproducible(S):
     assert np.array_equal(outs[0][2], outs[1][2])
 
 
+# ------------------------------------------------------------------ persistent cooperative restart-cycle kernel
+@pytest.mark.parametrize("dims,restart,max_it,rtol", [((64, 64, 1), 30, 50, 1e-10),     # two cycles: 30 + 20 steps (config 1's inner options)
+                                                      ((40, 36, 1), 30, 7, 1e-30),      # one short cycle, cut by max_it
+                                                      ((128, 256, 1), 10, 35, 1e-12),   # four cycles, several virtual blocks
+                                                      ((16, 16, 1), 30, 400, 1e-9),     # converges inside a cycle
+                                                      ((16, 12, 20), 30, 40, 1e-10),    # 3-D, 7 diagonals
+                                                      ((362, 364, 1), 30, 31, 1e-14)])  # 131 768 rows: config 1's block size class
+def test_persistent_cycle_kernel_bit_identical_inner_solve(S, monkeypatch, dims, restart, max_it, rtol):
+    """cycle_coop.cuh: one cooperative kernel per restart cycle against one kernel per phase — same iterate, same
+    iteration count, same reason, same residual norm, bit for bit (reductions are formed over the same virtual grids)."""
+    m, n, p = dims
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MSPLIT_COOP", mode)
+        e = S.Engine(m, n, p, max_restart=restart)
+        assert e.spmv_format()[0] == "cdia"
+        assert e.persistent_cycles() == (mode == "1")
+        rec = []
+        for _ in range(3):  # successive inner solves from the previous iterate (nonzero guess), as the outer loops do
+            its, reason, rn = e.inner_solver(S.ksp_opts(restart=restart, max_it=max_it, rtol=rtol, abstol=1e-100))
+            rec.append((its, reason, rn, e.x.copy()))
+        out[mode] = rec
+        e.close()
+    for a, b in zip(out["0"], out["1"]):
+        assert a[0] == b[0] and a[1] == b[1]
+        assert a[2] == b[2]
+        assert np.array_equal(a[3], b[3])
+    assert out["0"][0][0] > 0
+
+
+@pytest.mark.parametrize("alg,dims,G,s,max_it", [("SM", (64, 64, 1), 2, 0, 50), ("SMSM_GLOBAL", (96, 64, 1), 2, 4, 12),
+                                                 ("SMSM_SEMI_LOCAL", (64, 48, 1), 4, 3, 20), ("SMSM_LOCAL", (16, 16, 16), 2, 3, 8),
+                                                 ("AMAM_GLOBAL", (64, 64, 1), 2, 3, 5)])
+def test_persistent_cycle_kernel_bit_identical_drivers(S, monkeypatch, alg, dims, G, s, max_it):
+    """Whole outer loops (deferred status reads, boundary layers published to the neighbours by the cycle kernel itself,
+    several engines sharing one GPU): histories and solutions bit-identical, a fraction of the launches."""
+    m, n, p = dims
+    asynchronous = alg.startswith("A")
+
+    def run(mode):
+        monkeypatch.setenv("MSPLIT_COOP", mode)
+        grp = S.Group(m, n, p, nblocks=G, s=s, max_restart=30)
+        assert all(e.persistent_cycles() == (mode == "1") for e in grp.engines)
+        kw = dict(periods=[1] * G) if asynchronous else {}  # the deterministic schedule for the asynchronous driver
+        res = grp.solve(alg, s=s, rtol=1e-7, inner=S.ksp_opts(restart=30, max_it=max_it, rtol=1e-10, abstol=1e-100), max_outer=60, **kw)
+        out = (res[0]["outer_its"], res[0]["hist"].copy(), grp.solution(), res[0]["kernel_launches"], res[0]["inner_its_total"])
+        grp.close()
+        return out
+
+    a, b = run("0"), run("1")
+    if asynchronous:
+        a2 = run("0")
+        if not (a[0] == a2[0] and np.array_equal(a[2], a2[2])):
+            pytest.skip("the scheduled asynchronous run is not bit-reproducible on this box: nothing to compare bit for bit")
+    assert a[0] == b[0] and a[4] == b[4]
+    assert np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2])
+    if not asynchronous:  # (the asynchronous driver does not report its launches)
+        assert b[3] < a[3] / 2
+
+
+def test_persistent_cycle_kernel_is_the_default_for_small_blocks(S, monkeypatch):
+    monkeypatch.delenv("MSPLIT_COOP", raising=False)
+    monkeypatch.delenv("MSPLIT_COOP_MAX_ROWS", raising=False)
+    e = S.Engine(64, 64)
+    assert e.persistent_cycles()
+    e.close()
+    e = S.Engine(33, 31)   # far diagonals at +-31: not the stencil view, one kernel per phase
+    assert not e.persistent_cycles()
+    e.close()
+    # all blocks in one process: two engines share the GPU side by side, more than two keep one kernel per phase
+    for G, expect in ((2, True), (4, False)):
+        grp = S.Group(64, 64, nblocks=G)
+        assert all(e.persistent_cycles() == expect for e in grp.engines)
+        grp.close()
+    monkeypatch.setenv("MSPLIT_COOP_MAX_ROWS", "1000")
+    e = S.Engine(64, 64)
+    assert not e.persistent_cycles()
+    e.close()
+
+
 def test_one_line_blocks(S, oracle):
     """Edge case: every block is a single grid line, so each row couples to both neighbours."""
     inner = dict(restart=30, max_it=4, rtol=1e-10, abstol=1e-100)
