@@ -26,6 +26,7 @@
 // reason -100, later launches return at once and the host turns it into an error (never a hang).
 #pragma once
 
+#include <cstdio>
 #define MSPK_COOP_TIMEOUT_NS 8000000000ull
 #define MSPK_COOP_REASON_ABORT (-100)
 
@@ -53,6 +54,20 @@ __device__ __forceinline__ unsigned long long coop_globaltimer() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// fence.acq_rel is all a release / acquire pattern around a relaxed access needs; __threadfence() is the sequentially
+// consistent fence (MEMBAR.SC.GPU)
+__device__ __forceinline__ void coop_fence() {
+#ifdef MSPK_COOP_SC_FENCE
+  __threadfence();
+#else
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+}
+#ifdef MSPK_COOP_TIMING // debug build only: block 0 accumulates the time it spends per phase and prints it per launch
+#define COOP_T(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const unsigned long long t_ = coop_globaltimer(); tacc[k] += t_ - tlast; tlast = t_; } } while (0)
+#else
+#define COOP_T(k) do { } while (0)
+#endif
 __device__ __forceinline__ double2 coop_ld2(const double *p) { return __ldcg(reinterpret_cast<const double2 *>(p)); }
 
 // grid-wide barrier; false = aborted (timeout here or in another block).  bar[0] counts arrivals and only ever grows:
@@ -62,7 +77,7 @@ __device__ __forceinline__ bool coop_barrier(unsigned int *bar, unsigned int &ta
   target += gridDim.x;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence(); // release: this block's stores (ordered before by the block barrier) are visible before its arrival
+    coop_fence(); // release: this block's stores (ordered before by the block barrier) are visible before its arrival
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     int aborted = 0;
     unsigned int polls = 0;
@@ -77,7 +92,7 @@ __device__ __forceinline__ bool coop_barrier(unsigned int *bar, unsigned int &ta
         else if (t - t0 > MSPK_COOP_TIMEOUT_NS) { atomicExch(bar + 1, 1u); aborted = 1; break; }
       }
     }
-    __threadfence(); // acquire: nothing of this block is read before the other blocks' arrivals were seen
+    coop_fence(); // acquire: nothing of this block is read before the other blocks' arrivals were seen
     *s_flag = aborted;
   }
   __syncthreads();
@@ -153,53 +168,62 @@ __device__ MSPK_COOP_PHASE double coop_sum_partials(const double *partial, int n
   return block_sum(v, red);
 }
 // P2: block partials of <w, vtilde_v>, v < nv.  The rows are split over the virtual x-grid of k_mdot (gx blocks: the partial
-// of a vector depends on that split only, not on which vectors share a thread), the vectors in chunks of MSPK_COOP_NV;
-// work item = (chunk, virtual block)
+// of a vector depends on that split only, not on which vectors share a thread).  Work item = (virtual block, group of vector
+// chunks): the chunks of MSPK_COOP_NV vectors are dealt out so that there are about as many items as resident blocks — a
+// whole virtual block per item (w loaded once, ONE pair of block barriers) when gx already fills the grid, a few chunks per
+// item when the block is so small that gx does not.
 __device__ MSPK_COOP_PHASE void coop_phase_mdot(const double *V, long long ld, const double *w, int nb, int nv, int gx, double *partial, double *sm) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const long long npairs = nb >> 1;
   const long long stride = (long long)gx * MSPK_THREADS;
   const int nchunks = (nv + MSPK_COOP_NV - 1) / MSPK_COOP_NV;
-  for (int item = blockIdx.x; item < gx * nchunks; item += gridDim.x) {
-    const int c = item / gx, vbx = item - c * gx;
-    const int v0 = c * MSPK_COOP_NV;
-    const int nvc = min(MSPK_COOP_NV, nv - v0);
-    const double *Vc = V + (long long)v0 * ld;
-    double acc[MSPK_COOP_NV];
+  int ngrp = (int)gridDim.x / gx; // groups of chunks per virtual block
+  ngrp = ngrp < 1 ? 1 : (ngrp > nchunks ? nchunks : ngrp);
+  const int cpg = (nchunks + ngrp - 1) / ngrp; // chunks per group
+  ngrp = (nchunks + cpg - 1) / cpg;
+  for (int item = blockIdx.x; item < gx * ngrp; item += gridDim.x) {
+    const int grp = item / gx, vbx = item - grp * gx;
+    const int vfirst = grp * cpg * MSPK_COOP_NV;
+    const int vend = min(nv, vfirst + cpg * MSPK_COOP_NV);
+    for (int v0 = vfirst; v0 < vend; v0 += MSPK_COOP_NV) {
+      const int nvc = min(MSPK_COOP_NV, vend - v0);
+      const double *Vc = V + (long long)v0 * ld;
+      double acc[MSPK_COOP_NV];
 #pragma unroll
-    for (int v = 0; v < MSPK_COOP_NV; v++) acc[v] = 0.0;
-    for (long long p = vbx * (long long)MSPK_THREADS + tid; p < npairs; p += stride) {
-      const double2 w0 = coop_ld2(w + 2 * p);
-      double2 xv[MSPK_COOP_NV];
+      for (int v = 0; v < MSPK_COOP_NV; v++) acc[v] = 0.0;
+      for (long long p = vbx * (long long)MSPK_THREADS + tid; p < npairs; p += stride) {
+        const double2 w0 = coop_ld2(w + 2 * p);
+        double2 xv[MSPK_COOP_NV];
 #pragma unroll
-      for (int v = 0; v < MSPK_COOP_NV; v++)
-        if (v < nvc) xv[v] = coop_ld2(Vc + v * ld + 2 * p);
+        for (int v = 0; v < MSPK_COOP_NV; v++)
+          if (v < nvc) xv[v] = coop_ld2(Vc + v * ld + 2 * p);
 #pragma unroll
-      for (int v = 0; v < MSPK_COOP_NV; v++)
+        for (int v = 0; v < MSPK_COOP_NV; v++)
+          if (v < nvc) {
+            acc[v] = fma(xv[v].x, w0.x, acc[v]);
+            acc[v] = fma(xv[v].y, w0.y, acc[v]);
+          }
+      }
+      if ((nb & 1) && vbx == 0 && tid == 0) {
+        const double wl = __ldcg(w + nb - 1);
+#pragma unroll
+        for (int v = 0; v < MSPK_COOP_NV; v++)
+          if (v < nvc) acc[v] = fma(__ldcg(Vc + v * ld + nb - 1), wl, acc[v]);
+      }
+#pragma unroll
+      for (int v = 0; v < MSPK_COOP_NV; v++) {
         if (v < nvc) {
-          acc[v] = fma(xv[v].x, w0.x, acc[v]);
-          acc[v] = fma(xv[v].y, w0.y, acc[v]);
+          const double ws_ = warp_sum(acc[v]);
+          if (lane == 0) sm[wid * (MSPK_MAXK + 2) + (v0 - vfirst) + v] = ws_;
         }
-    }
-    if ((nb & 1) && vbx == 0 && tid == 0) {
-      const double wl = __ldcg(w + nb - 1);
-#pragma unroll
-      for (int v = 0; v < MSPK_COOP_NV; v++)
-        if (v < nvc) acc[v] = fma(__ldcg(Vc + v * ld + nb - 1), wl, acc[v]);
-    }
-#pragma unroll
-    for (int v = 0; v < MSPK_COOP_NV; v++) {
-      if (v < nvc) {
-        const double ws_ = warp_sum(acc[v]);
-        if (lane == 0) sm[wid * MSPK_COOP_NV + v] = ws_;
       }
     }
     __syncthreads();
-    if (tid < nvc) {
+    if (tid < vend - vfirst) { // thread v adds the eight warp sums of vector vfirst + v in warp order
       double bs = 0.0;
 #pragma unroll
-      for (int ww = 0; ww < MSPK_THREADS / 32; ww++) bs += sm[ww * MSPK_COOP_NV + tid];
-      partial[(64 + v0 + tid) * (long long)MSPK_MAX_PART + vbx] = bs;
+      for (int ww = 0; ww < MSPK_THREADS / 32; ww++) bs += sm[ww * (MSPK_MAXK + 2) + tid];
+      partial[(64 + vfirst + tid) * (long long)MSPK_MAX_PART + vbx] = bs;
     }
     __syncthreads();
   }
@@ -282,7 +306,7 @@ __device__ MSPK_COOP_PHASE void coop_phase_update_x(const double *V, long long l
 template <int ND>
 __global__ void __launch_bounds__(MSPK_THREADS, 2) k_gmres_cycle_coop(CycleCoopArgs a) {
   __shared__ GmresCtl sc;
-  __shared__ double sm[(MSPK_THREADS / 32) * MSPK_COOP_NV];
+  __shared__ double sm[(MSPK_THREADS / 32) * (MSPK_MAXK + 2)];
   __shared__ double cf[MSPK_MAXK + 2];
   __shared__ double red[32];
   __shared__ int s_flag;
@@ -294,6 +318,9 @@ __global__ void __launch_bounds__(MSPK_THREADS, 2) k_gmres_cycle_coop(CycleCoopA
     return;
   }
   unsigned int bar_target = coop_ld_relaxed(a.bar + 2); // arrivals counted by the earlier launches
+#ifdef MSPK_COOP_TIMING
+  unsigned long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = coop_globaltimer();
+#endif
   // ---- private copy of the control block (everything but the Hessenberg columns, which this cycle rewrites before use)
   {
     const unsigned long long *src = reinterpret_cast<const unsigned long long *>(a.ctl);
@@ -328,25 +355,40 @@ __global__ void __launch_bounds__(MSPK_THREADS, 2) k_gmres_cycle_coop(CycleCoopA
       sp.x = a.V + (long long)it * a.ld; sp.y = w; sp.b = nullptr;
       coop_phase_spmv<ND>(sp, sc.inv_arr[it]);
     }
+    COOP_T(1);
     if (!coop_barrier(a.bar, bar_target, &s_flag)) goto aborted;
+    COOP_T(2);
     // ---- P2: lhh = -V^T w
     const MdotGeom gm = mdot_geometry(a.nb, nv, a.mdot_gmax, a.num_sms);
     coop_phase_mdot(a.V, a.ld, w, a.nb, nv, gm.gx, a.ws.partial, sm);
+    COOP_T(3);
     if (!coop_barrier(a.bar, bar_target, &s_flag)) goto aborted;
+    COOP_T(4);
     coop_phase_mdot_final(a.ws.partial, nv, gm.gx, sc.inv_arr, sc.lhh);
     __syncthreads();
     for (int j = tid; j < nv; j += MSPK_THREADS) cf[j] = sc.lhh[j] * sc.inv_arr[j];
     __syncthreads();
+    COOP_T(5);
     // ---- P3: w += V lhh, ||w||; Hessenberg / Givens update, KSPConvergedDefault, next `active`
     coop_phase_maxpy(a.V, a.ld, w, a.nb, nv, a.vg_maxpy, cf, a.ws.partial, red);
+    COOP_T(6);
     if (!coop_barrier(a.bar, bar_target, &s_flag)) goto aborted;
+    COOP_T(7);
     {
       const double tot = coop_sum_partials(a.ws.partial, a.vg_maxpy, red);
-      if (tid == 0) ctl_cgs_pass_end(&sc, sqrt(tot), 0);
+      COOP_T(8);
+      // ctl_cgs_pass_end for REFINE_NEVER (the only case this kernel takes): hh[j] = 0 - lhh[j] element by element (the
+      // sum of squares it also forms only decides about a second pass), then the step is closed by one thread
+      if (tid == 0) red[0] = sqrt(tot);
+      for (int j = tid; j <= it; j += MSPK_THREADS) sc.hh[(size_t)it * (MSPK_MAXK + 2) + j] = 0.0 - sc.lhh[j];
+      __syncthreads();
+      if (tid == 0) { sc.refine = 0; ctl_step_end(&sc, red[0]); }
       __syncthreads();
     }
+    COOP_T(9);
   }
 
+  COOP_T(0);
   // ---- KSPGMRESBuildSoln: back substitution (every block, on its own copy), x += sum_j nrs_j v_j, boundary publication
   {
     const int cols = sc.it; // Hessenberg columns this cycle wrote (ctl_build_soln may reset `it` on a zero pivot)
@@ -367,6 +409,12 @@ __global__ void __launch_bounds__(MSPK_THREADS, 2) k_gmres_cycle_coop(CycleCoopA
       if (tid == 0) a.bar[2] = bar_target; // where the next launch starts counting
     }
   }
+#ifdef MSPK_COOP_TIMING
+  COOP_T(10);
+  if (blockIdx.x == 0 && tid == 0 && a.nsteps >= 30)
+    printf("COOPT steps %d ns: prologue+exit %llu | spmv %llu bar1 %llu | mdot %llu bar2 %llu final %llu | maxpy %llu bar3 %llu sum %llu ctl %llu | update_x %llu\n", sc.it,
+           tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7], tacc[8], tacc[9], tacc[10]);
+#endif
   return;
 
 aborted:
