@@ -1,5 +1,5 @@
 """Small end-to-end run touching every kernel (for compute-sanitizer): sync + async drivers, TSQR and LSQR minimisers,
-refinement/MGS variants, 2-D and 3-D, stand-alone GMRES, raw op wrappers."""
+refinement/MGS variants, 2-D and 3-D, the persistent cycle kernel, stand-alone GMRES, raw op wrappers."""
 import os
 import sys
 
@@ -14,6 +14,16 @@ for alg, s in (("SM", 0), ("SMSM_GLOBAL", 3), ("SMSM_SEMI_LOCAL", 3), ("SMSM_LOC
     r = g.solve(alg, s=s, rtol=1e-4, inner=inner, max_outer=30)
     print(alg, r[0]["outer_its"], r[0]["final_residual"] / r[0]["norm0"])
     g.close()
+# stencil-shaped strips (grid columns a multiple of 4): the coded-DIA stencil SpMV and, forced, the persistent cooperative
+# restart-cycle kernel (csrc/cycle_coop.cuh) on three engines sharing the GPU, 2-D and 3-D
+os.environ["MSPLIT_COOP"] = "1"
+for shape, nblocks in (((24, 16, 1), 3), ((8, 4, 6), 2)):
+    g = S.Group(*shape, nblocks=nblocks, s=3, max_restart=10)
+    assert all(e.persistent_cycles() for e in g.engines)
+    r = g.solve("SMSM_GLOBAL", s=3, rtol=1e-4, inner=inner, max_outer=30)
+    print("persistent cycles", shape, r[0]["outer_its"], r[0]["final_residual"] / r[0]["norm0"])
+    g.close()
+del os.environ["MSPLIT_COOP"]
 g = S.Group(6, 5, 8, nblocks=2, s=3, max_restart=10)
 print("3d", g.solve("SMSM_GLOBAL", s=3, rtol=1e-4, inner=inner, max_outer=20)[0]["outer_its"])
 g.close()
