@@ -413,7 +413,7 @@ static bool coop_eligible(const msp_engine *e, const msp_ksp_opts *o, int cgs_re
   if (e->coop_mode == 2 && e->nb > e->coop_max_rows) return false;
   return ((((uintptr_t)e->x | (uintptr_t)e->V | (uintptr_t)e->rhs) & 31) == 0);
 }
-// one restart cycle of at most nsteps steps as ONE launch
+// one restart cycle of at most nsteps steps as ONE launch; 0 = enqueued, 1 = error, 2 = not launchable here (nothing enqueued)
 static int launch_cycle_coop(msp_engine *e, int nsteps, double *peer_lo, double *peer_hi) {
   CycleCoopArgs a{};
   a.sp = spmv_args(e, e->x, e->V);
@@ -424,7 +424,15 @@ static int launch_cycle_coop(msp_engine *e, int nsteps, double *peer_lo, double 
   a.ws = e->ws; a.bar = e->coop_bar;
   void *args[] = {&a};
   const void *fn = (e->dia.nd == 5) ? (const void *)k_gmres_cycle_coop<5> : (const void *)k_gmres_cycle_coop<7>;
-  CK(cudaLaunchCooperativeKernel(fn, dim3(e->coop_grid), dim3(MSPK_THREADS), args, 0, e->st));
+  const cudaError_t er = cudaLaunchCooperativeKernel(fn, dim3(e->coop_grid), dim3(MSPK_THREADS), args, 0, e->st);
+  if (er == cudaErrorCooperativeLaunchTooLarge || er == cudaErrorNotSupported || er == cudaErrorLaunchOutOfResources) {
+    // the device cannot hold the grid (SMs taken away by MPS / MIG / a debugger): nothing was enqueued; this engine keeps
+    // one kernel per phase from here on (still the GPU path, same iterates)
+    cudaGetLastError();
+    e->coop_mode = 0;
+    return 2;
+  }
+  CK(er);
   e->launches++;
   return 0;
 }

@@ -243,11 +243,17 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
       CK(cudaMemcpyAsync(e->hsc + 32, reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, its), 16, cudaMemcpyDeviceToHost, e->st));
       return 0;
     };
+    bool cycle_enqueued = false;
     if (coop_eligible(e, o, cgs_refine, from_rhs)) {
       // small block: the whole cycle is one persistent cooperative kernel (cycle_coop.cuh), bit-identical to the launches below
-      RC(launch_cycle_coop(e, nsteps, peer_lo, peer_hi));
-      CK(cudaMemcpyAsync(e->hsc + 32, reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, its), 16, cudaMemcpyDeviceToHost, e->st));
-    } else if (e->use_graphs && !e->prof) {
+      const int rc = launch_cycle_coop(e, nsteps, peer_lo, peer_hi);
+      if (rc == 1) return 1;
+      if (rc == 0) {
+        CK(cudaMemcpyAsync(e->hsc + 32, reinterpret_cast<char *>(e->ctl) + offsetof(GmresCtl, its), 16, cudaMemcpyDeviceToHost, e->st));
+        cycle_enqueued = true;
+      }
+    }
+    if (!cycle_enqueued && e->use_graphs && !e->prof) {
       const msp_engine::CycleKey key(nsteps, cgs_refine + 4 * (o->mgs ? 1 : 0), from_rhs ? 1 : 0, (const void *)e->V, (const void *)peer_lo, (const void *)peer_hi);
       auto itg = e->cycle_graphs.find(key);
       if (itg == e->cycle_graphs.end()) {
@@ -267,7 +273,7 @@ static int op_inner_solve(msp_engine *e, const msp_ksp_opts *o, bool publish, in
       }
       CK(cudaGraphLaunch(itg->second.exec, e->st));
       e->launches += itg->second.launches;
-    } else {
+    } else if (!cycle_enqueued) {
       RC(enqueue_cycle());
     }
     first = false;
