@@ -172,7 +172,7 @@ int msp_spmv_format(const msp_engine *e, int *width);
 /* 1 when this engine runs each GMRES restart cycle (KSPGMRESCycle: the loop inside inner_solver utils.c:950-970) as ONE
  * persistent cooperative kernel with grid barriers instead of one kernel per phase — chosen for small blocks, where the
  * phases are launch-bound; the iterates are bit-identical either way.  Needs the coded-DIA stencil view, one GPU per
- * Jacobi block, classical Gram-Schmidt without refinement.  Environment: MSPLIT_COOP=0 never, MSPLIT_COOP=1 for every
+ * Jacobi block, classical Gram-Schmidt (any refinement type; modified Gram-Schmidt keeps one kernel per phase).  Environment: MSPLIT_COOP=0 never, MSPLIT_COOP=1 for every
  * eligible block, default: blocks of at most MSPLIT_COOP_MAX_ROWS rows. */
 int msp_persistent_cycles(const msp_engine *e);
 int64_t msp_mat_nnz(msp_engine *e, int which);

@@ -358,36 +358,44 @@ __global__ void __launch_bounds__(MSPK_THREADS, 2) k_gmres_cycle_coop(CycleCoopA
     COOP_T(1);
     if (!coop_barrier(a.bar, bar_target, &s_flag)) goto aborted;
     COOP_T(2);
-    // ---- P2: lhh = -V^T w
-    const MdotGeom gm = mdot_geometry(a.nb, nv, a.mdot_gmax, a.num_sms);
-    coop_phase_mdot(a.V, a.ld, w, a.nb, nv, gm.gx, a.ws.partial, sm);
-    COOP_T(3);
-    if (!coop_barrier(a.bar, bar_target, &s_flag)) goto aborted;
-    COOP_T(4);
-    coop_phase_mdot_final(a.ws.partial, nv, gm.gx, sc.inv_arr, sc.lhh);
-    __syncthreads();
-    for (int j = tid; j < nv; j += MSPK_THREADS) cf[j] = sc.lhh[j] * sc.inv_arr[j];
-    __syncthreads();
-    COOP_T(5);
-    // ---- P3: w += V lhh, ||w||; Hessenberg / Givens update, KSPConvergedDefault, next `active`
-    coop_phase_maxpy(a.V, a.ld, w, a.nb, nv, a.vg_maxpy, cf, a.ws.partial, red);
-    COOP_T(6);
-    if (!coop_barrier(a.bar, bar_target, &s_flag)) goto aborted;
-    COOP_T(7);
-    {
-      const double tot = coop_sum_partials(a.ws.partial, a.vg_maxpy, red);
-      COOP_T(8);
-      // ctl_cgs_pass_end for REFINE_NEVER (the only case this kernel takes): hh[j] = 0 - lhh[j] element by element (the
-      // sum of squares it also forms only decides about a second pass), then the step is closed by one thread
-      if (tid == 0) red[0] = sqrt(tot);
-      for (int j = tid; j <= it; j += MSPK_THREADS) sc.hh[(size_t)it * (MSPK_MAXK + 2) + j] = 0.0 - sc.lhh[j];
+    // classical Gram-Schmidt: one pass, or two with -ksp_gmres_cgs_refinement_type refine_always / refine_ifneeded (the
+    // decision of the first pass, ctl->refine, is the same in every block)
+    for (int pass = 0; pass < 2; pass++) {
+      if (pass == 1 && !sc.refine) break;
+      // ---- P2: lhh = -V^T w
+      const MdotGeom gm = mdot_geometry(a.nb, nv, a.mdot_gmax, a.num_sms);
+      coop_phase_mdot(a.V, a.ld, w, a.nb, nv, gm.gx, a.ws.partial, sm);
+      COOP_T(3);
+      if (!coop_barrier(a.bar, bar_target, &s_flag)) goto aborted;
+      COOP_T(4);
+      coop_phase_mdot_final(a.ws.partial, nv, gm.gx, sc.inv_arr, sc.lhh);
       __syncthreads();
-      if (tid == 0) { sc.refine = 0; ctl_step_end(&sc, red[0]); }
+      for (int j = tid; j < nv; j += MSPK_THREADS) cf[j] = sc.lhh[j] * sc.inv_arr[j];
       __syncthreads();
+      COOP_T(5);
+      // ---- P3: w += V lhh, ||w||; Hessenberg / Givens update, KSPConvergedDefault, next `active`
+      coop_phase_maxpy(a.V, a.ld, w, a.nb, nv, a.vg_maxpy, cf, a.ws.partial, red);
+      COOP_T(6);
+      if (!coop_barrier(a.bar, bar_target, &s_flag)) goto aborted;
+      COOP_T(7);
+      {
+        const double tot = coop_sum_partials(a.ws.partial, a.vg_maxpy, red);
+        COOP_T(8);
+        if (sc.cgs_refine == 0) {
+          // ctl_cgs_pass_end for REFINE_NEVER: hh[j] = 0 - lhh[j] element by element (the sum of squares it also forms
+          // only decides about a second pass), then the step is closed by one thread
+          if (tid == 0) red[0] = sqrt(tot);
+          for (int j = tid; j <= it; j += MSPK_THREADS) sc.hh[(size_t)it * (MSPK_MAXK + 2) + j] = 0.0 - sc.lhh[j];
+          __syncthreads();
+          if (tid == 0) { sc.refine = 0; ctl_step_end(&sc, red[0]); }
+        } else if (tid == 0) {
+          ctl_cgs_pass_end(&sc, sqrt(tot), pass); // asks for the second pass (ctl->refine) or closes the step
+        }
+        __syncthreads();
+      }
+      COOP_T(9);
     }
-    COOP_T(9);
   }
-
   COOP_T(0);
   // ---- KSPGMRESBuildSoln: back substitution (every block, on its own copy), x += sum_j nrs_j v_j, boundary publication
   {

@@ -409,7 +409,8 @@ static int coop_setup(msp_engine *e) {
   return 0;
 }
 static bool coop_eligible(const msp_engine *e, const msp_ksp_opts *o, int cgs_refine, bool from_rhs) {
-  if (!e->coop_mode || e->prof || from_rhs || o->mgs || cgs_refine) return false;
+  (void)cgs_refine; // both CGS refinement types run inside the cycle kernel (a second MDot / MAXPY pass per step)
+  if (!e->coop_mode || e->prof || from_rhs || o->mgs) return false;
   if (e->coop_mode == 2 && e->nb > e->coop_max_rows) return false;
   return ((((uintptr_t)e->x | (uintptr_t)e->V | (uintptr_t)e->rhs) & 31) == 0);
 }

@@ -654,13 +654,16 @@ def test_run_to_run_bitwise_reproducible(S):
 
 
 # ------------------------------------------------------------------ persistent cooperative restart-cycle kernel
-@pytest.mark.parametrize("dims,restart,max_it,rtol", [((64, 64, 1), 30, 50, 1e-10),     # two cycles: 30 + 20 steps (config 1's inner options)
-                                                      ((40, 36, 1), 30, 7, 1e-30),      # one short cycle, cut by max_it
-                                                      ((128, 256, 1), 10, 35, 1e-12),   # four cycles, several virtual blocks
-                                                      ((16, 16, 1), 30, 400, 1e-9),     # converges inside a cycle
-                                                      ((16, 12, 20), 30, 40, 1e-10),    # 3-D, 7 diagonals
-                                                      ((362, 364, 1), 30, 31, 1e-14)])  # 131 768 rows: config 1's block size class
-def test_persistent_cycle_kernel_bit_identical_inner_solve(S, monkeypatch, dims, restart, max_it, rtol):
+@pytest.mark.parametrize("dims,restart,max_it,rtol,refine", [((64, 64, 1), 30, 50, 1e-10, 0),     # two cycles: 30 + 20 steps (config 1's inner options)
+                                                             ((40, 36, 1), 30, 7, 1e-30, 0),      # one short cycle, cut by max_it
+                                                             ((128, 256, 1), 10, 35, 1e-12, 0),   # four cycles, several virtual blocks
+                                                             ((16, 16, 1), 30, 400, 1e-9, 0),     # converges inside a cycle
+                                                             ((16, 12, 20), 30, 40, 1e-10, 0),    # 3-D, 7 diagonals
+                                                             ((362, 364, 1), 30, 31, 1e-14, 0),   # 131 768 rows: config 1's block size class
+                                                             ((64, 48, 1), 20, 45, 1e-11, 2),     # REFINE_ALWAYS: two CGS passes per step
+                                                             ((48, 64, 1), 30, 60, 1e-12, 1),     # REFINE_IFNEEDED: the second pass decided on the device
+                                                             ((12, 16, 12), 12, 30, 1e-10, 2)])   # 3-D with refinement
+def test_persistent_cycle_kernel_bit_identical_inner_solve(S, monkeypatch, dims, restart, max_it, rtol, refine):
     """cycle_coop.cuh: one cooperative kernel per restart cycle against one kernel per phase — same iterate, same
     iteration count, same reason, same residual norm, bit for bit (reductions are formed over the same virtual grids)."""
     m, n, p = dims
@@ -672,7 +675,7 @@ def test_persistent_cycle_kernel_bit_identical_inner_solve(S, monkeypatch, dims,
         assert e.persistent_cycles() == (mode == "1")
         rec = []
         for _ in range(3):  # successive inner solves from the previous iterate (nonzero guess), as the outer loops do
-            its, reason, rn = e.inner_solver(S.ksp_opts(restart=restart, max_it=max_it, rtol=rtol, abstol=1e-100))
+            its, reason, rn = e.inner_solver(S.ksp_opts(restart=restart, max_it=max_it, rtol=rtol, abstol=1e-100, cgs_refine=refine))
             rec.append((its, reason, rn, e.x.copy()))
         out[mode] = rec
         e.close()
