@@ -5,7 +5,8 @@
 // x += V y with the boundary publication of comm_sync_send_and_receive comm.c:126-141) by one launch whose phases are
 // separated by grid-wide barriers.  At 131 072 rows per block (BASELINE config 1) a phase moves 1-30 MB out of L2 in 1-3 us
 // and the one-kernel-per-phase path is bound by launch and drain latency (8-10 us per launch); here a step costs three
-// barriers instead of three launches.
+// barriers instead of three launches (five with a second Gram-Schmidt pass: -ksp_gmres_cgs_refinement_type refine_always,
+// or refine_ifneeded when the first pass asks for it — decided on the device, identically in every block).
 //
 // Bit-identical to the one-kernel-per-phase path by construction:
 //  * per-row arithmetic (the SpMV fma chain over the sorted row, the MAXPY fma chain in vector order, x += V y) does not
@@ -21,9 +22,10 @@
 // SpMV trip) — L1 is not coherent between SMs inside one launch.
 //
 // The barrier is a monotone arrival counter (fence + fire-and-forget relaxed reduction, relaxed polling + fence; the count a
-// launch starts from is left behind by the previous one).  All blocks must be co-resident: the kernel is launched with cudaLaunchCooperativeKernel.  A block
-// that waits longer than MSPK_COOP_TIMEOUT_NS raises the sticky abort word: every block leaves, the solve reports
-// reason -100, later launches return at once and the host turns it into an error (never a hang).
+// launch starts from is left behind by the previous one).  All blocks must be co-resident: the kernel is launched with
+// cudaLaunchCooperativeKernel.  A block that waits longer than MSPK_COOP_TIMEOUT_NS raises the sticky abort word: every
+// block leaves, the solve reports reason -100, later launches return at once and the host turns it into an error (never a
+// hang).  No kernel of one engine ever waits for a kernel of another engine.
 #pragma once
 
 #include <cstdio>
