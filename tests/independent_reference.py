@@ -35,10 +35,14 @@ def poisson3d(nx, ny, nz):
     return (sp.kron(iz, sp.kron(iy, lap(nx))) + sp.kron(iz, sp.kron(lap(ny), ix)) + sp.kron(lap(nz), sp.kron(iy, ix))).tocsr()
 
 
-def gmres_capped(A, b, x, restart=30, max_it=20, rtol=1e-10, abstol=1e-100):
+def gmres_capped(A, b, x, restart=30, max_it=20, rtol=1e-10, abstol=1e-100, refine=0):
     """Restarted GMRES as PETSc runs it inside inner_solver (utils.c:950-970): nonzero initial guess, tolerance relative to
     the INITIAL residual, no convergence verdict before the first iteration, stop after max_it iterations in total
-    (the iterate of the truncated cycle is kept).  Returns (x, iterations)."""
+    (the iterate of the truncated cycle is kept).  Returns (x, iterations).
+
+    refine: -ksp_gmres_cgs_refinement_type (tmp/petscmpiexec_help:607) — 0 refine_never, 2 refine_always (a second
+    classical Gram-Schmidt pass on the orthogonalised vector, its coefficients added to the Hessenberg column),
+    1 refine_ifneeded (the second pass only when the vector lost more than it kept: ||w_after|| < ||h||)."""
     its = 0
     r0norm = None
     while True:
@@ -57,8 +61,12 @@ def gmres_capped(A, b, x, restart=30, max_it=20, rtol=1e-10, abstol=1e-100):
         used = 0
         for j in range(k):
             w = A @ V[j]
-            h = V[: j + 1] @ w            # classical Gram-Schmidt, one pass
+            h = V[: j + 1] @ w            # classical Gram-Schmidt, first pass
             w = w - h @ V[: j + 1]
+            if refine == 2 or (refine == 1 and np.linalg.norm(w) < np.linalg.norm(h)):
+                h2 = V[: j + 1] @ w       # second pass on the already orthogonalised vector
+                w = w - h2 @ V[: j + 1]
+                h = h + h2
             H[: j + 1, j] = h
             H[j + 1, j] = np.linalg.norm(w)
             used = j + 1

@@ -51,6 +51,20 @@ def test_capped_gmres_matches_oracle_iterate():
         assert np.linalg.norm(xi - xo) <= 1e-9 * np.linalg.norm(xo)
 
 
+@pytest.mark.parametrize("refine", [1, 2])
+def test_gmres_with_cgs_refinement_matches_oracle(refine):
+    """-ksp_gmres_cgs_refinement_type refine_ifneeded / refine_always: same iteration count and iterate as the oracle."""
+    A = I.poisson2d(28, 24)
+    b = A @ np.ones(A.shape[0])
+    rp, ci, va = O.poisson2d(28, 24)
+    x0 = np.random.default_rng(11).standard_normal(A.shape[0])
+    for kw in (dict(restart=30, max_it=45, rtol=1e-12), dict(restart=12, max_it=10000, rtol=1e-8)):
+        xi, its_i = I.gmres_capped(A, b, x0.copy(), abstol=1e-100, refine=refine, **kw)
+        xo, its_o, reason, rn = O.gmres(rp, ci, va, b, x0=x0, abstol=1e-100, initial_rtol=1, guess_nonzero=1, cgs_refine=refine, **kw)
+        assert its_i == its_o, (kw, its_i, its_o)
+        assert np.linalg.norm(xi - xo) <= 1e-9 * np.linalg.norm(xo)
+
+
 def test_smsm_global_one_block_256():
     """VERDICT r01 point 1: 256^2, one block, s = 5, inner GMRES(30) capped at 20 -> 12 outer iterations, 6.07e-7."""
     n = 256
